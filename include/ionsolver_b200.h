@@ -1,0 +1,171 @@
+/* ionsolver_b200.h -- C ABI of libionsolver_b200.so
+ *
+ * Drop-in boundary for IonSolver's extended-LBM MHD time step on NVIDIA B200 (sm_100a).
+ * This header replaces what the reference's Rust host obtains from the `ocl` / `ocl-macros` crates and
+ * /root/reference/src/opencl.rs: one opaque device-side domain object per LbmDomain, its buffers, and one
+ * enqueue function per OpenCL kernel launch site.  Every entry point cites the reference call site it
+ * replaces (paths relative to /root/reference).  The cgo-style binding a maintainer adds on the Rust side is
+ * shown in INTEGRATION.md.
+ *
+ * Contract (same as an in-order OpenCL command queue, src/lbm/domain.rs:132-135):
+ *   - every ion_enqueue_* call is asynchronous and ordered on the domain's CUDA stream; ion_finish blocks;
+ *   - ion_buffer_read / ion_buffer_write are blocking with respect to the host pointer (like bread!/bwrite!);
+ *   - every function returns 0 on success or a non-zero IonStatus / cudaError_t value; the text of the last
+ *     failure on the calling thread is available from ion_last_error_string();
+ *   - there is NO CPU fallback: without a CUDA device of compute capability 10.x, ion_domain_create fails.
+ * Thread-compatibility: one thread per handle at a time; distinct handles may be used concurrently.
+ */
+#ifndef IONSOLVER_B200_H
+#define IONSOLVER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ION_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define ION_API __attribute__((visibility("default")))
+#else
+#define ION_API
+#endif
+
+/* enum discriminants are the reference's wire values (src/lbm/types.rs:17-25,55-60,76-82) */
+/* D3Q27 uses the canonical weights 8/27, 2/27, 1/54, 1/216: the reference emits no DEF_WC for D3Q27 and its kernels
+ * therefore never compiled for that set (domain.rs:766-768 vs sim_kernels.cl:192) */
+enum IonVelocitySet { ION_D2Q9 = 0, ION_D3Q15 = 1, ION_D3Q19 = 2, ION_D3Q27 = 3 };
+enum IonRelaxationTime { ION_SRT = 0, ION_TRT = 1 };
+enum IonFloatType { ION_FP16S = 0, ION_FP16C = 1, ION_FP32 = 2 };
+/* src/lbm/types.rs:105-111 */
+enum IonTransferField { ION_TRANSFER_FI = 0, ION_TRANSFER_RHO_U_FLAGS = 1, ION_TRANSFER_EI = 2, ION_TRANSFER_QI = 3 };
+
+/* extension switches: the `#define`s emitted at src/lbm/domain.rs:834-856 */
+enum IonExt {
+    ION_EXT_EQUILIBRIUM_BOUNDARIES = 1u << 0,
+    ION_EXT_VOLUME_FORCE = 1u << 1,
+    ION_EXT_FORCE_FIELD = 1u << 2,
+    ION_EXT_MAGNETO_HYDRO = 1u << 3,
+    ION_EXT_SUBGRID_ECR = 1u << 4,
+    ION_EXT_UPDATE_FIELDS = 1u << 5 /* graphics_active => UPDATE_FIELDS, domain.rs:856 */
+};
+
+/* flag bits, src/lbm/domain.rs:819-828 (runtime values, not the IDE placeholders of sim_kernels.cl:45-54) */
+#define ION_TYPE_S 0x01
+#define ION_TYPE_E 0x02
+#define ION_TYPE_C 0x04
+#define ION_TYPE_F 0x08
+#define ION_TYPE_M 0x10
+#define ION_TYPE_BO 0x1F
+
+/* Device buffers of one domain, src/lbm/domain.rs:45-74 / SURVEY.md appendix A */
+enum IonField {
+    ION_FIELD_FI = 0,     /* Q*n  f32|u16 */
+    ION_FIELD_RHO = 1,    /* n    f32, initial 1.0 */
+    ION_FIELD_U = 2,      /* 3n   f32 (x,y,z planes) */
+    ION_FIELD_FLAGS = 3,  /* n    u8 */
+    ION_FIELD_F = 4,      /* 3n   f32, ext_force_field */
+    ION_FIELD_E_STAT = 5, /* 3n   f32, MHD */
+    ION_FIELD_B_STAT = 6,
+    ION_FIELD_E_DYN = 7,
+    ION_FIELD_B_DYN = 8,
+    ION_FIELD_FQI = 9,     /* 7n   f32|u16, MHD */
+    ION_FIELD_EI = 10,     /* Q*n  f32|u16, MHD */
+    ION_FIELD_Q = 11,      /* n    f32, MHD */
+    ION_FIELD_QU_LOD = 12, /* 4*n_lod f32 AoS (q,ux,uy,uz), MHD */
+    ION_FIELD_E_VAR = 13,  /* 3n   f32, SUBGRID_ECR */
+    ION_FIELD_ETI = 14,    /* 7n   f32|u16, SUBGRID_ECR */
+    ION_FIELD_ET = 15,     /* n    f32, SUBGRID_ECR */
+    ION_FIELD_TRANSFER_P = 16, /* A_max*max(17,T*s) bytes, layout [b*A+a] (sim_kernels.cl:1069) */
+    ION_FIELD_TRANSFER_M = 17,
+    ION_FIELD_COUNT = 18
+};
+
+enum IonStatus {
+    ION_OK = 0,
+    ION_ERR_INVALID = 10001,     /* bad argument / params */
+    ION_ERR_UNSUPPORTED = 10002, /* configuration the reference cannot build either (e.g. MHD on D2Q9) */
+    ION_ERR_NO_DEVICE = 10003,   /* no sm_100 device: there is no CPU fallback */
+    ION_ERR_ABSENT = 10004,      /* buffer not allocated for this configuration (Option::None in domain.rs) */
+    ION_ERR_RANGE = 10005        /* offset/size outside the buffer */
+};
+
+/* The compile-time parameters the reference injects as text (get_device_defines, src/lbm/domain.rs:736-858),
+ * as a plain struct.  Float members carry the exact f32 the reference prints with `{:?}`. */
+typedef struct IonParams {
+    uint32_t abi_version; /* ION_ABI_VERSION */
+    uint32_t nx, ny, nz;  /* DEF_NX/NY/NZ: local domain size incl. halo layers (domain.rs:91-93) */
+    uint32_t dx, dy, dz;  /* DEF_DX/DY/DZ: number of domains per axis */
+    uint32_t di;          /* DEF_DI: index of this domain */
+    int32_t ox, oy, oz;   /* DEF_OX/OY/OZ: signed origin offsets (domain.rs:101-103) */
+    uint32_t velocity_set;    /* IonVelocitySet */
+    uint32_t relaxation_time; /* IonRelaxationTime */
+    uint32_t float_type;      /* IonFloatType */
+    uint32_t ext;             /* IonExt bit mask */
+    float w;                  /* DEF_W = 1/(3 nu + 1/2) (domain.rs:808) */
+    float ke, kmu, kmu0, kkge, kimg, kvev, kme; /* DEF_KE..DEF_KME (domain.rs:838-844) */
+    float wq;                 /* DEF_WQ (domain.rs:848) */
+    float kkbme, keabs;       /* DEF_KKBME, DEF_KEABS (domain.rs:852-853) */
+    uint32_t lod_depth;       /* DEF_LOD_DEPTH */
+    uint32_t n_lod;           /* DEF_NUM_LOD */
+    uint32_t n_lod_own;       /* DEF_NUM_LOD_OWN */
+} IonParams;
+
+typedef struct ion_domain ion_domain_t;
+
+/* library / device ------------------------------------------------------------------------------------- */
+/* replaces opencl::device_selection (src/opencl.rs:9-63): number of usable sm_100 devices */
+ION_API int ion_device_count(int* count);
+ION_API const char* ion_last_error_string(void);
+ION_API uint32_t ion_abi_version(void);
+
+/* domain lifetime: LbmDomain::new program build + buffer allocation + kernel binding (domain.rs:88-409) */
+ION_API int ion_domain_create(const IonParams* params, int device, ion_domain_t** out);
+ION_API int ion_domain_destroy(ion_domain_t* dom); /* Drop of LbmDomain */
+ION_API int ion_domain_params(const ion_domain_t* dom, IonParams* out);
+
+/* buffers: buffer!/bwrite!/bread! and Buffer::read/write with .offset()/.len() (ocl-macros; e.g. domain.rs:504-511,
+ * mod.rs:460-462, setup.rs:180-302, file.rs:118-268).  Offsets and sizes are in BYTES. */
+ION_API int ion_buffer_size(const ion_domain_t* dom, int field, size_t* bytes);
+ION_API int ion_buffer_write(ion_domain_t* dom, int field, const void* host, size_t offset_bytes, size_t bytes);
+ION_API int ion_buffer_read(ion_domain_t* dom, int field, void* host, size_t offset_bytes, size_t bytes);
+/* raw device pointer (for zero-copy interop with the caller's CUDA allocator / torch tensors); NULL if absent */
+ION_API int ion_buffer_device_ptr(const ion_domain_t* dom, int field, void** dptr);
+/* device-to-device copy between two domains' buffers on dst's stream; the single-node replacement for the
+ * host-staged std::ptr::swap exchange of mod.rs:380-384 and the LOD slice copy of mod.rs:460-462 */
+ION_API int ion_buffer_copy(ion_domain_t* dst, int dst_field, size_t dst_offset_bytes, ion_domain_t* src, int src_field,
+                    size_t src_offset_bytes, size_t bytes);
+
+/* kernels: one per enqueue site ---------------------------------------------------------------------------- */
+ION_API int ion_enqueue_initialize(ion_domain_t* dom);                                          /* domain.rs:412-416 (ends with finish) */
+ION_API int ion_enqueue_stream_collide(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz); /* domain.rs:419-428 */
+ION_API int ion_enqueue_update_fields(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz);  /* domain.rs:432-441 */
+ION_API int ion_enqueue_update_e_b_dyn(ion_domain_t* dom);                                      /* domain.rs:443-451 */
+ION_API int ion_enqueue_lod_part_2_gather(ion_domain_t* dom);                                   /* domain.rs:453-462 */
+ION_API int ion_enqueue_clear_qu_lod(ion_domain_t* dom);                                        /* domain.rs:464-472 */
+/* transfer kernels only (the host read/write halves of domain.rs:484-543 are ion_buffer_read/write/copy on
+ * ION_FIELD_TRANSFER_P/M); direction 0,1,2 = x,y,z */
+ION_API int ion_enqueue_transfer_extract(ion_domain_t* dom, int transfer_field, uint32_t direction, uint64_t t); /* domain.rs:484-501 */
+ION_API int ion_enqueue_transfer_insert(ion_domain_t* dom, int transfer_field, uint32_t direction, uint64_t t);  /* domain.rs:532-542 */
+/* LbmDomain::voxelize_mesh_on_device (src/mesh.rs:281-343): p0/p1/p2 are 3*triangles floats, bbu the 7 floats of
+ * mesh.rs:288-295 (bit-cast triangle count, bbox-2, bbox+2) */
+ION_API int ion_voxelize_mesh(ion_domain_t* dom, const float* p0, const float* p1, const float* p2, uint32_t triangles,
+                      const float bbu[7], uint32_t direction, uint8_t flag, float mpc_x, float mpc_y, float mpc_z,
+                      uint64_t t);
+ION_API int ion_enqueue_precompute_b(ion_domain_t* dom);     /* domain.rs:551-556: psi_from_mesh + static_b_from_mesh */
+ION_API int ion_enqueue_precompute_e(ion_domain_t* dom);     /* domain.rs:558-567: static_e_from_mesh -> E_stat */
+ION_API int ion_enqueue_precompute_e_ecr(ion_domain_t* dom); /* domain.rs:569-578: static_e_from_mesh -> E_var */
+ION_API int ion_domain_set_ecr_freq(ion_domain_t* dom, float ecrf); /* kernel arg "ecrf", domain.rs:292-296 */
+ION_API int ion_finish(ion_domain_t* dom);                   /* queue.finish(), mod.rs:275-279 */
+
+/* instrumentation (no reference equivalent): kernels launched by this library since load, for bench.py */
+ION_API uint64_t ion_kernel_launch_count(void);
+/* the CUDA stream of a domain (cudaStream_t as void*), so callers can record CUDA events on it */
+ION_API int ion_domain_stream(const ion_domain_t* dom, void** stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IONSOLVER_B200_H */

@@ -1,0 +1,465 @@
+// api.cu -- the C ABI of libionsolver_b200.so (see include/ionsolver_b200.h for the reference call sites).
+//
+// One ion_domain_t = one LbmDomain of the reference (/root/reference/src/lbm/domain.rs:20-80): a CUDA device,
+// an in-order stream (the OpenCL queue), the buffers of domain.rs:151-211,311-322 and the kernel bindings.
+// No CPU fallback exists anywhere in this file: every compute entry point launches sm_100a kernels.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "lattice.cuh"
+
+namespace ion {
+// launchers implemented in the kernel translation units
+template <int VS>
+cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx, float fy, float fz,
+                                     cudaStream_t s);
+template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
+template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
+cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches);
+size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di);
+cudaError_t launch_clear_qu_lod(const KArgs& a, cudaStream_t s);
+cudaError_t launch_lod_gather(const KArgs& a, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_transfer(const KArgs& p, int vs, int fp, int transfer_field, int insert, uint32_t direction, uint64_t t,
+                            cudaStream_t s);
+cudaError_t launch_voxelize(const KArgs& a, uint32_t direction, uint8_t flag, const float* p0, const float* p1, const float* p2,
+                            uint32_t tri, const float* bb6, float mx, float my, float mz, int mhd, cudaStream_t s);
+size_t compaction_scratch_bytes(uint64_t N);
+cudaError_t count_sources(const KArgs& a, uint8_t mask, uint32_t* counts, uint32_t* host_total, cudaStream_t s);
+size_t field_source_bytes(uint32_t count);
+cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s);
+cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void* table, cudaStream_t s);
+
+__global__ void k_fill_f32(float* p, uint64_t n, float v) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+}  // namespace ion
+
+using namespace ion;
+
+struct ion_domain {
+    IonParams params;
+    int device;
+    cudaStream_t stream;
+    void* buf[ION_FIELD_COUNT];
+    size_t bytes[ION_FIELD_COUNT];
+    KArgs k;
+    void* lod_sources;   // scratch of update_e_b_dynamic
+    uint32_t* cp_counts; // scratch of the precompute compaction
+    float ecrf;
+};
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    return (int)e;
+}
+#define ION_CUDA(call)                                        \
+    do {                                                      \
+        cudaError_t ion_e_ = (call);                          \
+        if (ion_e_ != cudaSuccess) return cuda_fail(ion_e_, #call); \
+    } while (0)
+
+static int set_q(int vs, int* q, int* dim, int* tr) {
+    switch (vs) {
+        case ION_D2Q9: *q = 9; *dim = 2; *tr = 3; return 0;
+        case ION_D3Q15: *q = 15; *dim = 3; *tr = 5; return 0;
+        case ION_D3Q19: *q = 19; *dim = 3; *tr = 5; return 0;
+        case ION_D3Q27: *q = 27; *dim = 3; *tr = 9; return 0;
+    }
+    return -1;
+}
+
+extern "C" {
+
+const char* ion_last_error_string(void) { return g_err; }
+uint32_t ion_abi_version(void) { return ION_ABI_VERSION; }
+uint64_t ion_kernel_launch_count(void) { return g_launches.load(); }
+
+int ion_device_count(int* count) {
+    if (!count) return fail(ION_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    int usable = 0;
+    for (int d = 0; d < n; d++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) usable++;
+    }
+    *count = usable;
+    return ION_OK;
+}
+
+int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
+    if (!p || !out) return fail(ION_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    if (p->abi_version != ION_ABI_VERSION) return fail(ION_ERR_INVALID, "IonParams.abi_version %u != %u", p->abi_version, ION_ABI_VERSION);
+    int q, dim, tr;
+    if (set_q((int)p->velocity_set, &q, &dim, &tr)) return fail(ION_ERR_INVALID, "unknown velocity_set %u", p->velocity_set);
+    if (p->relaxation_time > ION_TRT || p->float_type > ION_FP32) return fail(ION_ERR_INVALID, "unknown relaxation_time/float_type");
+    if (!p->nx || !p->ny || !p->nz || !p->dx || !p->dy || !p->dz) return fail(ION_ERR_INVALID, "zero lattice or domain extent");
+    const uint64_t n = (uint64_t)p->nx * p->ny * p->nz;
+    if (n > 0xFFFFFFFFull) return fail(ION_ERR_UNSUPPORTED, "more than 2^32 cells per domain (cell index is uint, sim_kernels.cl:484)");
+    if (p->ny > 65535u || p->nz > 65535u) return fail(ION_ERR_UNSUPPORTED, "ny/nz exceed the CUDA grid limit 65535");
+    const bool mhd = p->ext & ION_EXT_MAGNETO_HYDRO, ecr = p->ext & ION_EXT_SUBGRID_ECR;
+    if (mhd) {
+        if (!(p->ext & ION_EXT_VOLUME_FORCE)) return fail(ION_ERR_UNSUPPORTED, "MAGNETO_HYDRO needs VOLUME_FORCE (c_tau, sim_kernels.cl:519,650)");
+        if (dim != 3) return fail(ION_ERR_UNSUPPORTED, "MAGNETO_HYDRO on D2Q9 divides by DEF_NZ/2^depth = 0 in the reference (sim_kernels.cl:431)");
+        if (p->lod_depth > 4u) return fail(ION_ERR_UNSUPPORTED, "mhd_lod_depth > 4 shifts by >= 32 bits in the reference (sim_kernels.cl:908)");
+        const uint32_t nd = 1u << p->lod_depth;
+        if (p->nx < nd || p->ny < nd || p->nz < nd) return fail(ION_ERR_UNSUPPORTED, "domain smaller than 2^lod_depth cells: lod_index divides by zero (sim_kernels.cl:429)");
+        if (p->n_lod_own == 0 || p->n_lod < p->n_lod_own) return fail(ION_ERR_INVALID, "bad LOD counts");
+        if ((uint64_t)(p->nx + 2u) * (p->ny + 2u) * (p->nz + 2u) > 3ull * n) return fail(ION_ERR_UNSUPPORTED, "padded psi grid does not fit the E_dyn scratch (sim_kernels.cl:1234, domain.rs:280)");
+    }
+    if (ecr) return fail(ION_ERR_UNSUPPORTED, "SUBGRID_ECR is not built yet (SURVEY section 8 row f3)");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) return fail(ION_ERR_NO_DEVICE, "no CUDA device (%s); there is no CPU fallback", cudaGetErrorName(ce));
+    if (device < 0 || device >= ndev) return fail(ION_ERR_INVALID, "device %d out of range (%d devices)", device, ndev);
+    int major = 0;
+    ION_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return fail(ION_ERR_NO_DEVICE, "device %d has compute capability %d.x; kernels are built for sm_100a only", device, major);
+    ION_CUDA(cudaSetDevice(device));
+
+    ion_domain* d = new (std::nothrow) ion_domain();
+    if (!d) return fail(ION_ERR_INVALID, "out of host memory");
+    memset(d, 0, sizeof(*d));
+    d->params = *p;
+    d->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete d; return cuda_fail(e, "cudaStreamCreate"); }
+
+    const size_t s = p->float_type == ION_FP32 ? 4 : 2;
+    size_t* B = d->bytes;
+    B[ION_FIELD_FI] = n * q * s;  // domain.rs:151-158
+    B[ION_FIELD_RHO] = n * 4;
+    B[ION_FIELD_U] = n * 12;
+    B[ION_FIELD_FLAGS] = n;
+    if (p->ext & ION_EXT_FORCE_FIELD) B[ION_FIELD_F] = n * 12;  // domain.rs:168
+    if (mhd) {                                                   // domain.rs:172-193
+        B[ION_FIELD_E_STAT] = B[ION_FIELD_B_STAT] = B[ION_FIELD_E_DYN] = B[ION_FIELD_B_DYN] = n * 12;
+        B[ION_FIELD_FQI] = n * 7 * s;
+        B[ION_FIELD_EI] = n * q * s;
+        B[ION_FIELD_Q] = n * 4;
+        B[ION_FIELD_QU_LOD] = (size_t)p->n_lod * 16;
+    }
+    size_t a_max = 0;  // domain.rs:311-318
+    if (p->dx > 1) a_max = a_max > (size_t)p->ny * p->nz ? a_max : (size_t)p->ny * p->nz;
+    if (p->dy > 1) a_max = a_max > (size_t)p->nx * p->nz ? a_max : (size_t)p->nx * p->nz;
+    if (p->dz > 1) a_max = a_max > (size_t)p->nx * p->ny ? a_max : (size_t)p->nx * p->ny;
+    const size_t per = (size_t)tr * s > 17 ? (size_t)tr * s : 17;
+    B[ION_FIELD_TRANSFER_P] = B[ION_FIELD_TRANSFER_M] = a_max * per;
+
+    for (int f = 0; f < ION_FIELD_COUNT; f++) {
+        if (!B[f]) continue;
+        e = cudaMalloc(&d->buf[f], B[f]);
+        if (e == cudaSuccess) e = cudaMemsetAsync(d->buf[f], 0, B[f], d->stream);
+        if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc/cudaMemset of a domain buffer"); }
+    }
+    k_fill_f32<<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>((float*)d->buf[ION_FIELD_RHO], n, 1.0f);  // rho = 1, domain.rs:156
+    g_launches++;
+    if (mhd) {
+        e = cudaMalloc(&d->lod_sources, lod_source_bytes(p->lod_depth, p->n_lod_own, p->dx, p->dy, p->dz, p->di));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d->cp_counts, compaction_scratch_bytes(n));
+        if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc scratch"); }
+    }
+
+    KArgs& k = d->k;
+    k.fi = d->buf[ION_FIELD_FI];
+    k.rho = (float*)d->buf[ION_FIELD_RHO];
+    k.u = (float*)d->buf[ION_FIELD_U];
+    k.flags = (uint8_t*)d->buf[ION_FIELD_FLAGS];
+    k.F = (const float*)d->buf[ION_FIELD_F];
+    k.E_stat = (float*)d->buf[ION_FIELD_E_STAT];
+    k.B_stat = (float*)d->buf[ION_FIELD_B_STAT];
+    k.E_dyn = (float*)d->buf[ION_FIELD_E_DYN];
+    k.B_dyn = (float*)d->buf[ION_FIELD_B_DYN];
+    k.fqi = d->buf[ION_FIELD_FQI];
+    k.ei = d->buf[ION_FIELD_EI];
+    k.Q = (float*)d->buf[ION_FIELD_Q];
+    k.QU_lod = (float*)d->buf[ION_FIELD_QU_LOD];
+    k.E_var = (const float*)d->buf[ION_FIELD_E_VAR];
+    k.eti = d->buf[ION_FIELD_ETI];
+    k.Et = (float*)d->buf[ION_FIELD_ET];
+    k.transfer_p = (uint8_t*)d->buf[ION_FIELD_TRANSFER_P];
+    k.transfer_m = (uint8_t*)d->buf[ION_FIELD_TRANSFER_M];
+    k.N = n;
+    k.nx = p->nx; k.ny = p->ny; k.nz = p->nz;
+    k.dx = p->dx; k.dy = p->dy; k.dz = p->dz; k.di = p->di;
+    k.ox = p->ox; k.oy = p->oy; k.oz = p->oz;
+    k.ext = p->ext;
+    k.w = p->w;
+    k.ke = p->ke; k.kmu = p->kmu; k.kmu0 = p->kmu0; k.kkge = p->kkge; k.kme = p->kme; k.wq = p->wq;
+    k.kkbme = p->kkbme; k.keabs = p->keabs;
+    k.lod_depth = p->lod_depth; k.n_lod = p->n_lod; k.n_lod_own = p->n_lod_own;
+    k.ecrf = 0.0f;
+    e = cudaStreamSynchronize(d->stream);
+    if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "domain initialisation"); }
+    *out = d;
+    return ION_OK;
+}
+
+int ion_domain_destroy(ion_domain_t* d) {
+    if (!d) return ION_OK;
+    cudaSetDevice(d->device);
+    if (d->stream) cudaStreamSynchronize(d->stream);
+    for (int f = 0; f < ION_FIELD_COUNT; f++)
+        if (d->buf[f]) cudaFree(d->buf[f]);
+    if (d->lod_sources) cudaFree(d->lod_sources);
+    if (d->cp_counts) cudaFree(d->cp_counts);
+    if (d->stream) cudaStreamDestroy(d->stream);
+    delete d;
+    return ION_OK;
+}
+
+int ion_domain_params(const ion_domain_t* d, IonParams* out) {
+    if (!d || !out) return fail(ION_ERR_INVALID, "NULL argument");
+    *out = d->params;
+    return ION_OK;
+}
+int ion_domain_stream(const ion_domain_t* d, void** stream) {
+    if (!d || !stream) return fail(ION_ERR_INVALID, "NULL argument");
+    *stream = (void*)d->stream;
+    return ION_OK;
+}
+
+static int check_field(const ion_domain_t* d, int field) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (field < 0 || field >= ION_FIELD_COUNT) return fail(ION_ERR_INVALID, "field id %d out of range", field);
+    if (!d->buf[field]) return fail(ION_ERR_ABSENT, "buffer %d is not allocated for this configuration", field);
+    return ION_OK;
+}
+
+int ion_buffer_size(const ion_domain_t* d, int field, size_t* bytes) {
+    if (!d || !bytes) return fail(ION_ERR_INVALID, "NULL argument");
+    if (field < 0 || field >= ION_FIELD_COUNT) return fail(ION_ERR_INVALID, "field id %d out of range", field);
+    *bytes = d->bytes[field];
+    return ION_OK;
+}
+int ion_buffer_device_ptr(const ion_domain_t* d, int field, void** dptr) {
+    if (!d || !dptr) return fail(ION_ERR_INVALID, "NULL argument");
+    if (field < 0 || field >= ION_FIELD_COUNT) return fail(ION_ERR_INVALID, "field id %d out of range", field);
+    *dptr = d->buf[field];
+    return ION_OK;
+}
+int ion_buffer_write(ion_domain_t* d, int field, const void* host, size_t off, size_t bytes) {
+    int r = check_field(d, field);
+    if (r) return r;
+    if (!host && bytes) return fail(ION_ERR_INVALID, "NULL host pointer");
+    if (off > d->bytes[field] || bytes > d->bytes[field] - off) return fail(ION_ERR_RANGE, "write of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, off, field, d->bytes[field]);
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaMemcpyAsync((char*)d->buf[field] + off, host, bytes, cudaMemcpyHostToDevice, d->stream));
+    ION_CUDA(cudaStreamSynchronize(d->stream));
+    return ION_OK;
+}
+int ion_buffer_read(ion_domain_t* d, int field, void* host, size_t off, size_t bytes) {
+    int r = check_field(d, field);
+    if (r) return r;
+    if (!host && bytes) return fail(ION_ERR_INVALID, "NULL host pointer");
+    if (off > d->bytes[field] || bytes > d->bytes[field] - off) return fail(ION_ERR_RANGE, "read of %zu bytes at %zu exceeds buffer %d (%zu bytes)", bytes, off, field, d->bytes[field]);
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaMemcpyAsync(host, (const char*)d->buf[field] + off, bytes, cudaMemcpyDeviceToHost, d->stream));
+    ION_CUDA(cudaStreamSynchronize(d->stream));
+    return ION_OK;
+}
+int ion_buffer_copy(ion_domain_t* dst, int df, size_t doff, ion_domain_t* src, int sf, size_t soff, size_t bytes) {
+    int r = check_field(dst, df);
+    if (r) return r;
+    r = check_field(src, sf);
+    if (r) return r;
+    if (doff > dst->bytes[df] || bytes > dst->bytes[df] - doff || soff > src->bytes[sf] || bytes > src->bytes[sf] - soff)
+        return fail(ION_ERR_RANGE, "device copy out of range");
+    ION_CUDA(cudaSetDevice(dst->device));
+    if (src->stream != dst->stream) {  // order after everything already queued on the source domain
+        cudaEvent_t ev;
+        ION_CUDA(cudaSetDevice(src->device));
+        ION_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ION_CUDA(cudaEventRecord(ev, src->stream));
+        ION_CUDA(cudaSetDevice(dst->device));
+        ION_CUDA(cudaStreamWaitEvent(dst->stream, ev, 0));
+        ION_CUDA(cudaEventDestroy(ev));
+    }
+    if (src->device == dst->device)
+        ION_CUDA(cudaMemcpyAsync((char*)dst->buf[df] + doff, (const char*)src->buf[sf] + soff, bytes, cudaMemcpyDeviceToDevice, dst->stream));
+    else
+        ION_CUDA(cudaMemcpyPeerAsync((char*)dst->buf[df] + doff, dst->device, (const char*)src->buf[sf] + soff, src->device, bytes, dst->stream));
+    return ION_OK;
+}
+
+#define ION_VS_DISPATCH(fn, ...)                                                 \
+    switch (d->params.velocity_set) {                                            \
+        case ION_D2Q9: e = fn<ION_D2Q9>(__VA_ARGS__); break;                     \
+        case ION_D3Q15: e = fn<ION_D3Q15>(__VA_ARGS__); break;                   \
+        case ION_D3Q19: e = fn<ION_D3Q19>(__VA_ARGS__); break;                   \
+        default: e = fn<ION_D3Q27>(__VA_ARGS__); break;                          \
+    }
+
+int ion_enqueue_initialize(ion_domain_t* d) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    ION_CUDA(cudaSetDevice(d->device));
+    cudaError_t e;
+    const bool mhd = d->params.ext & ION_EXT_MAGNETO_HYDRO;
+    ION_VS_DISPATCH(launch_initialize_vs, d->k, (int)d->params.float_type, mhd, d->stream)
+    g_launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "initialize launch");
+    ION_CUDA(cudaStreamSynchronize(d->stream));  // enqueue_initialize ends with queue.finish(), domain.rs:415
+    return ION_OK;
+}
+
+int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, float fz) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    ION_CUDA(cudaSetDevice(d->device));
+    cudaError_t e;
+    const bool mhd = d->params.ext & ION_EXT_MAGNETO_HYDRO;
+    const bool trt = d->params.relaxation_time == ION_TRT;
+    ION_VS_DISPATCH(launch_stream_collide_vs, d->k, (int)d->params.float_type, mhd, trt, t, fx, fy, fz, d->stream)
+    g_launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "stream_collide launch");
+    return ION_OK;
+}
+
+int ion_enqueue_update_fields(ion_domain_t* d, uint64_t t, float fx, float fy, float fz) {
+    (void)fx; (void)fy; (void)fz;  // bound but unused by the reference kernel too (sim_kernels.cl:834-859)
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    ION_CUDA(cudaSetDevice(d->device));
+    cudaError_t e;
+    ION_VS_DISPATCH(launch_update_fields_vs, d->k, (int)d->params.float_type, t, d->stream)
+    g_launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "update_fields launch");
+    return ION_OK;
+}
+
+static int need_mhd(const ion_domain_t* d) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (!(d->params.ext & ION_EXT_MAGNETO_HYDRO)) return fail(ION_ERR_ABSENT, "kernel needs ext_magneto_hydro (Option::None in domain.rs:30-35)");
+    return ION_OK;
+}
+
+int ion_enqueue_update_e_b_dyn(ion_domain_t* d) {
+    int r = need_mhd(d);
+    if (r) return r;
+    ION_CUDA(cudaSetDevice(d->device));
+    uint64_t l = 0;
+    cudaError_t e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l);
+    g_launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "update_e_b_dynamic launch");
+    return ION_OK;
+}
+int ion_enqueue_lod_part_2_gather(ion_domain_t* d) {
+    int r = need_mhd(d);
+    if (r) return r;
+    ION_CUDA(cudaSetDevice(d->device));
+    uint64_t l = 0;
+    cudaError_t e = launch_lod_gather(d->k, d->stream, &l);
+    g_launches += l;
+    if (e != cudaSuccess) return cuda_fail(e, "lod_part_2_gather launch");
+    return ION_OK;
+}
+int ion_enqueue_clear_qu_lod(ion_domain_t* d) {
+    int r = need_mhd(d);
+    if (r) return r;
+    ION_CUDA(cudaSetDevice(d->device));
+    cudaError_t e = launch_clear_qu_lod(d->k, d->stream);
+    g_launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "clear_qu_lod launch");
+    return ION_OK;
+}
+
+static int transfer(ion_domain_t* d, int field, int insert, uint32_t direction, uint64_t t) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (field < ION_TRANSFER_FI || field > ION_TRANSFER_QI) return fail(ION_ERR_INVALID, "unknown transfer field %d", field);
+    const uint32_t dims = d->params.velocity_set == ION_D2Q9 ? 2u : 3u;
+    if (direction >= dims) return fail(ION_ERR_INVALID, "direction %u out of range", direction);
+    const uint32_t dd = direction == 0 ? d->params.dx : direction == 1 ? d->params.dy : d->params.dz;
+    if (dd <= 1 || !d->buf[ION_FIELD_TRANSFER_P]) return fail(ION_ERR_ABSENT, "axis %u is not split: no transfer buffers (domain.rs:311-318)", direction);
+    if ((field == ION_TRANSFER_EI || field == ION_TRANSFER_QI) && !(d->params.ext & ION_EXT_MAGNETO_HYDRO))
+        return fail(ION_ERR_ABSENT, "transfer kernel needs ext_magneto_hydro (domain.rs:340-367)");
+    ION_CUDA(cudaSetDevice(d->device));
+    cudaError_t e = launch_transfer(d->k, (int)d->params.velocity_set, (int)d->params.float_type, field, insert, direction, t, d->stream);
+    g_launches++;
+    if (e != cudaSuccess) return cuda_fail(e, "transfer launch");
+    return ION_OK;
+}
+int ion_enqueue_transfer_extract(ion_domain_t* d, int field, uint32_t direction, uint64_t t) { return transfer(d, field, 0, direction, t); }
+int ion_enqueue_transfer_insert(ion_domain_t* d, int field, uint32_t direction, uint64_t t) { return transfer(d, field, 1, direction, t); }
+
+int ion_voxelize_mesh(ion_domain_t* d, const float* p0, const float* p1, const float* p2, uint32_t triangles, const float bbu[7],
+                      uint32_t direction, uint8_t flag, float mx, float my, float mz, uint64_t t) {
+    (void)t;  // bound as kernel arg "t" (mesh.rs:317) but never read by voxelize_mesh
+    if (!d || !p0 || !p1 || !p2 || !bbu) return fail(ION_ERR_INVALID, "NULL argument");
+    if (direction > 2) return fail(ION_ERR_INVALID, "direction %u out of range", direction);
+    uint32_t tn;
+    memcpy(&tn, &bbu[0], 4);
+    if (tn != triangles) return fail(ION_ERR_INVALID, "bbu[0] (bit-cast triangle count %u) disagrees with triangles=%u", tn, triangles);
+    ION_CUDA(cudaSetDevice(d->device));
+    float* dp = nullptr;  // p0|p1|p2 re-allocated per mesh like mesh.rs:282-287
+    const size_t bytes = (size_t)triangles * 3 * sizeof(float);
+    ION_CUDA(cudaMallocAsync((void**)&dp, 3 * bytes + 16, d->stream));
+    ION_CUDA(cudaMemcpyAsync(dp, p0, bytes, cudaMemcpyHostToDevice, d->stream));
+    ION_CUDA(cudaMemcpyAsync(dp + 3 * (size_t)triangles, p1, bytes, cudaMemcpyHostToDevice, d->stream));
+    ION_CUDA(cudaMemcpyAsync(dp + 6 * (size_t)triangles, p2, bytes, cudaMemcpyHostToDevice, d->stream));
+    const int mhd = (d->params.ext & ION_EXT_MAGNETO_HYDRO) ? 1 : 0;
+    cudaError_t e = launch_voxelize(d->k, direction, flag, dp, dp + 3 * (size_t)triangles, dp + 6 * (size_t)triangles, triangles, bbu + 1,
+                                    mx, my, mz, mhd, d->stream);
+    g_launches++;
+    cudaFreeAsync(dp, d->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "voxelize_mesh launch");
+    ION_CUDA(cudaStreamSynchronize(d->stream));  // host triangle arrays are borrowed only for the duration of the call
+    return ION_OK;
+}
+
+static int precompute(ion_domain_t* d, int which) {
+    int r = need_mhd(d);
+    if (r) return r;
+    ION_CUDA(cudaSetDevice(d->device));
+    const uint8_t mask = which == 0 ? ION_TYPE_M : (ION_TYPE_F | ION_TYPE_C);
+    uint32_t total = 0;
+    cudaError_t e = count_sources(d->k, mask, d->cp_counts, &total, d->stream);
+    g_launches += 2;
+    if (e != cudaSuccess) return cuda_fail(e, "source count");
+    void* table = nullptr;
+    ION_CUDA(cudaMallocAsync(&table, field_source_bytes(total), d->stream));
+    if (which == 0) {
+        e = launch_precompute_b(d->k, d->cp_counts, table, d->stream);
+        g_launches += 5;
+    } else {
+        float* E = which == 1 ? d->k.E_stat : (float*)d->buf[ION_FIELD_E_VAR];
+        if (!E) { cudaFreeAsync(table, d->stream); return fail(ION_ERR_ABSENT, "E_var needs ext_subgrid_ecr (domain.rs:573)"); }
+        e = launch_precompute_e(d->k, E, d->cp_counts, table, d->stream);
+        g_launches += 4;
+    }
+    cudaFreeAsync(table, d->stream);
+    if (e != cudaSuccess) return cuda_fail(e, "static field precompute launch");
+    return ION_OK;
+}
+int ion_enqueue_precompute_b(ion_domain_t* d) { return precompute(d, 0); }
+int ion_enqueue_precompute_e(ion_domain_t* d) { return precompute(d, 1); }
+int ion_enqueue_precompute_e_ecr(ion_domain_t* d) { return precompute(d, 2); }
+
+int ion_domain_set_ecr_freq(ion_domain_t* d, float ecrf) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    d->k.ecrf = ecrf;
+    return ION_OK;
+}
+
+int ion_finish(ion_domain_t* d) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaStreamSynchronize(d->stream));
+    return ION_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,317 @@
+// lattice.cuh -- device-side building blocks shared by all IonSolver-B200 kernels.
+//
+// Hand-written for sm_100a.  Written from the reference's *behaviour* (file:line citations into
+// /root/reference/src/kernels/sim_kernels.cl = "sim.cl"), not from its text: the velocity sets, weights and
+// operation ORDER of every floating-point expression are reproduced so that results are bit-identical to the
+// reference kernels compiled without contraction (the library is built with -fmad=false; every fused
+// multiply-add below is an explicit fmaf, exactly where the reference calls fma()).
+#pragma once
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#include "../../include/ionsolver_b200.h"
+
+namespace ion {
+
+// ------------------------------------------------------------------------------------------------------
+// kernel argument block (plain pointers + the IonParams subset the device needs)
+// ------------------------------------------------------------------------------------------------------
+struct KArgs {
+    void* fi;
+    float* rho;
+    float* u;
+    uint8_t* flags;
+    const float* F;
+    float* E_stat;
+    float* B_stat;
+    float* E_dyn;
+    float* B_dyn;
+    void* fqi;
+    void* ei;
+    float* Q;
+    float* QU_lod;
+    const float* E_var;
+    void* eti;
+    float* Et;
+    uint8_t* transfer_p;
+    uint8_t* transfer_m;
+    uint64_t N;  // DEF_N
+    uint32_t nx, ny, nz;
+    uint32_t dx, dy, dz, di;
+    int32_t ox, oy, oz;
+    uint32_t ext;
+    float w;
+    float ke, kmu, kmu0, kkge, kme, wq, kkbme, keabs;
+    uint32_t lod_depth, n_lod, n_lod_own;
+    float ecrf;
+};
+
+__device__ __forceinline__ float sq(float x) { return x * x; }
+__device__ __forceinline__ float cb(float x) { return x * x * x; }
+// OpenCL clamp(x,lo,hi) = fmin(fmax(x,lo),hi)
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+
+#define ION_DEF_C 0.57735027f  // lattice speed of sound, domain.rs:807
+
+// ------------------------------------------------------------------------------------------------------
+// velocity sets: direction table sim.cl:326-347, weights domain.rs:757-768, transfers types.rs:28-46
+// ------------------------------------------------------------------------------------------------------
+template <int VS> struct VSet;
+template <> struct VSet<ION_D2Q9> { static constexpr int Q = 9, DIM = 2, T = 3; };
+template <> struct VSet<ION_D3Q15> { static constexpr int Q = 15, DIM = 3, T = 5; };
+template <> struct VSet<ION_D3Q19> { static constexpr int Q = 19, DIM = 3, T = 5; };
+template <> struct VSet<ION_D3Q27> { static constexpr int Q = 27, DIM = 3, T = 9; };
+
+// c(axis, i): lattice velocity component; folded to an immediate once the callers' loops are unrolled
+template <int VS> __host__ __device__ __forceinline__ constexpr int cvel(int axis, int i) {
+    if (VS == ION_D2Q9) {
+        constexpr int c[3][9] = {{0, 1, -1, 0, 0, 1, -1, 1, -1}, {0, 0, 0, 1, -1, 1, -1, -1, 1}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+        return c[axis][i < 9 ? i : 0];
+    } else if (VS == ION_D3Q15) {
+        constexpr int c[3][15] = {{0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 1, -1, -1, 1},
+                                  {0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, -1, 1, 1, -1},
+                                  {0, 0, 0, 0, 0, 1, -1, 1, -1, -1, 1, 1, -1, 1, -1}};
+        return c[axis][i < 15 ? i : 0];
+    } else if (VS == ION_D3Q19) {
+        constexpr int c[3][19] = {{0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0},
+                                  {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, 1, -1, -1, 1, 0, 0, 1, -1},
+                                  {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, -1, 1, -1, 1}};
+        return c[axis][i < 19 ? i : 0];
+    } else {
+        constexpr int c[3][27] = {
+            {0, 1, -1, 0, 0, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, 1, -1, 1, -1, 1, -1, -1, 1},
+            {0, 0, 0, 1, -1, 0, 0, 1, -1, 0, 0, 1, -1, -1, 1, 0, 0, 1, -1, 1, -1, 1, -1, -1, 1, 1, -1},
+            {0, 0, 0, 0, 0, 1, -1, 0, 0, 1, -1, 1, -1, 0, 0, -1, 1, -1, 1, 1, -1, -1, 1, 1, -1, 1, -1}};
+        return c[axis][i < 27 ? i : 0];
+    }
+}
+
+// weight of direction i.  Class by number of non-zero components: 0 -> W0, 1 -> WS, 2 -> WE, 3 -> WC.
+// D3Q27 uses the canonical 8/27, 2/27, 1/54, 1/216 (the reference cannot build D3Q27).
+template <int VS> __host__ __device__ __forceinline__ constexpr float wclass(int nonzero) {
+    if (VS == ION_D2Q9) return nonzero == 0 ? (1.0f / 2.25f) : nonzero == 1 ? (1.0f / 9.0f) : (1.0f / 36.0f);
+    if (VS == ION_D3Q15) return nonzero == 0 ? (1.0f / 4.5f) : nonzero == 1 ? (1.0f / 9.0f) : (1.0f / 72.0f);
+    if (VS == ION_D3Q19) return nonzero == 0 ? (1.0f / 3.0f) : nonzero == 1 ? (1.0f / 18.0f) : (1.0f / 36.0f);
+    return nonzero == 0 ? (1.0f / 3.375f) : nonzero == 1 ? (1.0f / 13.5f) : nonzero == 2 ? (1.0f / 54.0f) : (1.0f / 216.0f);
+}
+template <int VS> __host__ __device__ __forceinline__ constexpr int nonzero(int i) {
+    return (cvel<VS>(0, i) != 0) + (cvel<VS>(1, i) != 0) + (cvel<VS>(2, i) != 0);
+}
+template <int VS> __host__ __device__ __forceinline__ constexpr float wdir(int i) { return wclass<VS>(nonzero<VS>(i)); }
+
+// sum_k c_k(i) * a_k evaluated left to right over the non-zero components (bit-equal to the reference's
+// `c(i)*ax+c(Q+i)*ay+c(2Q+i)*az` because multiplications by +-1 are exact and adding the +-0 products is an identity)
+template <int VS> __device__ __forceinline__ float cdot(int i, float ax, float ay, float az) {
+    const int cx = cvel<VS>(0, i), cy = cvel<VS>(1, i), cz = cvel<VS>(2, i);
+    float s = 0.0f;
+    bool first = true;
+    if (cx != 0) { s = cx > 0 ? ax : -ax; first = false; }
+    if (cy != 0) { const float t = cy > 0 ? ay : -ay; s = first ? t : s + t; first = false; }
+    if (cz != 0) { const float t = cz > 0 ? az : -az; s = first ? t : s + t; first = false; }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// DDF storage codecs: FP32 plain, FP16S (domain.rs:773-776), FP16C (sim.cl:79-90)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint16_t fp16c_encode(float x) {  // 1-4-11 custom format
+    const uint32_t b = __float_as_uint(x) + 0x00000800u;
+    const uint32_t e = (b & 0x7F800000u) >> 23;
+    const uint32_t m = b & 0x007FFFFFu;
+    return (uint16_t)((b & 0x80000000u) >> 16 | (uint32_t)(e > 112u) * ((((e - 112u) << 11) & 0x7800u) | m >> 12) |
+                      (uint32_t)((e < 113u) & (e > 100u)) * ((((0x007FF800u + m) >> (124u - e)) + 1u) >> 1));
+}
+__device__ __forceinline__ float fp16c_decode(uint16_t x) {
+    const uint32_t e = (x & 0x7800u) >> 11;
+    const uint32_t m = ((uint32_t)x & 0x07FFu) << 12;
+    const uint32_t v = __float_as_uint((float)m) >> 23;
+    return __uint_as_float(((uint32_t)x & 0x8000u) << 16 | (uint32_t)(e != 0u) * ((e + 112u) << 23 | m) |
+                           (uint32_t)((e == 0u) & (m != 0u)) * ((v - 37u) << 23 | ((m << (150u - v)) & 0x007FF000u)));
+}
+
+template <int FP> struct Codec;
+template <> struct Codec<ION_FP32> {
+    typedef float store_t;
+    static __device__ __forceinline__ float dec(float v) { return v; }
+    static __device__ __forceinline__ float enc(float v) { return v; }
+};
+template <> struct Codec<ION_FP16S> {
+    typedef uint16_t store_t;
+    static __device__ __forceinline__ float dec(uint16_t v) { return __half2float(__ushort_as_half(v)) * 3.0517578E-5f; }
+    static __device__ __forceinline__ uint16_t enc(float v) { return __half_as_ushort(__float2half_rn(v * 32768.0f)); }
+};
+template <> struct Codec<ION_FP16C> {
+    typedef uint16_t store_t;
+    static __device__ __forceinline__ float dec(uint16_t v) { return fp16c_decode(v); }
+    static __device__ __forceinline__ uint16_t enc(float v) { return fp16c_encode(v); }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// cell coordinates and periodic neighbours (sim.cl:134-148,248-302); one thread per cell, x fastest
+// ------------------------------------------------------------------------------------------------------
+struct Cell {
+    uint32_t x, y, z;
+    uint32_t n;                       // x+(y+z*ny)*nx
+    uint32_t x0, xp, xm, y0, yp, ym;  // sim.cl:250-255
+    uint32_t z0, zp, zm;              // sim.cl:256-258 (fits 32 bit: N <= 2^32)
+};
+
+__device__ __forceinline__ Cell make_cell(const KArgs& a, uint32_t x, uint32_t y, uint32_t z) {
+    Cell c;
+    c.x = x; c.y = y; c.z = z;
+    const uint32_t nx = a.nx, ny = a.ny, nz = a.nz;
+    c.x0 = x;
+    c.xp = (x + 1u == nx) ? 0u : x + 1u;
+    c.xm = (x == 0u) ? nx - 1u : x - 1u;
+    c.y0 = y * nx;
+    c.yp = ((y + 1u == ny) ? 0u : y + 1u) * nx;
+    c.ym = ((y == 0u) ? ny - 1u : y - 1u) * nx;
+    const uint32_t nxy = nx * ny;
+    c.z0 = z * nxy;
+    c.zp = ((z + 1u == nz) ? 0u : z + 1u) * nxy;
+    c.zm = ((z == 0u) ? nz - 1u : z - 1u) * nxy;
+    c.n = c.x0 + c.y0 + c.z0;
+    return c;
+}
+__device__ __forceinline__ Cell make_cell_n(const KArgs& a, uint32_t n) {  // coordinates(n), sim.cl:134-137
+    const uint32_t nxy = a.nx * a.ny;
+    const uint32_t t = n % nxy;
+    return make_cell(a, t % a.nx, t / a.nx, n / nxy);
+}
+__device__ __forceinline__ bool is_halo(const KArgs& a, uint32_t x, uint32_t y, uint32_t z) {  // sim.cl:145-148
+    return ((a.dx > 1u) & (x == 0u || x >= a.nx - 1u)) || ((a.dy > 1u) & (y == 0u || y >= a.ny - 1u)) ||
+           ((a.dz > 1u) & (z == 0u || z >= a.nz - 1u));
+}
+// j[i] of sim.cl:260-302.  D2Q9 ignores z exactly like the reference (sim.cl:265-268).
+template <int VS> __device__ __forceinline__ uint32_t neighbor(const Cell& c, int i) {
+    const int cx = cvel<VS>(0, i), cy = cvel<VS>(1, i), cz = cvel<VS>(2, i);
+    uint32_t j = (cx > 0 ? c.xp : cx < 0 ? c.xm : c.x0) + (cy > 0 ? c.yp : cy < 0 ? c.ym : c.y0);
+    if (VS != ION_D2Q9) j += (cz > 0 ? c.zp : cz < 0 ? c.zm : c.z0);
+    return i == 0 ? c.n : j;
+}
+// D3Q7 sub-lattice neighbours for the charge / temperature DDFs (neighbors_a, sim.cl:382-389)
+__device__ __forceinline__ uint32_t neighbor7(const Cell& c, int i) {
+    switch (i) {
+        case 1: return c.xp + c.y0 + c.z0;
+        case 2: return c.xm + c.y0 + c.z0;
+        case 3: return c.x0 + c.yp + c.z0;
+        case 4: return c.x0 + c.ym + c.z0;
+        case 5: return c.x0 + c.y0 + c.zp;
+        case 6: return c.x0 + c.y0 + c.zm;
+        default: return c.n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Esoteric-Pull in-place streaming (load_f/store_f sim.cl:234-247, load_a/store_a sim.cl:397-410).
+// SoA layout i*N+n (index_f, sim.cl:152-154).  Every (cell, slot) address is read and written by exactly one
+// thread per step, so the update is race-free without a second DDF copy.
+// ------------------------------------------------------------------------------------------------------
+template <int FP, int QQ, typename NB>
+__device__ __forceinline__ void ep_load(float* f, const void* buf, uint64_t N, uint32_t n, uint64_t todd, NB nb) {
+    typedef typename Codec<FP>::store_t S;
+    const S* p = reinterpret_cast<const S*>(buf);
+    f[0] = Codec<FP>::dec(p[n]);
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        f[i] = Codec<FP>::dec(p[(uint64_t)(i + 1 - (int)todd) * N + n]);          // t odd ? i : i+1
+        f[i + 1] = Codec<FP>::dec(p[(uint64_t)(i + (int)todd) * N + nb(i)]);      // t odd ? i+1 : i
+    }
+}
+template <int FP, int QQ, typename NB>
+__device__ __forceinline__ void ep_store(const float* f, void* buf, uint64_t N, uint32_t n, uint64_t todd, NB nb) {
+    typedef typename Codec<FP>::store_t S;
+    S* p = reinterpret_cast<S*>(buf);
+    p[n] = Codec<FP>::enc(f[0]);
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        p[(uint64_t)(i + (int)todd) * N + nb(i)] = Codec<FP>::enc(f[i]);          // t odd ? i+1 : i
+        p[(uint64_t)(i + 1 - (int)todd) * N + n] = Codec<FP>::enc(f[i + 1]);      // t odd ? i : i+1
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// moments, equilibrium, forcing
+// ------------------------------------------------------------------------------------------------------
+// calculate_rho_u, sim.cl:208-233: rho = (f0+f1+...)+1; momentum sums run over direction pairs in index
+// order, "+ then -" inside each pair, strictly left to right.
+template <int VS> __device__ __forceinline__ void rho_u(const float* f, float& rho, float& ux, float& uy, float& uz) {
+    constexpr int QQ = VSet<VS>::Q;
+    float r = f[0];
+#pragma unroll
+    for (int i = 1; i < QQ; i++) r += f[i];
+    r += 1.0f;
+    float m[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        bool first = true;
+#pragma unroll
+        for (int i = 1; i < QQ; i += 2) {
+            const int c = cvel<VS>(ax, i);
+            if (c != 0) {
+                const float plus = c > 0 ? f[i] : f[i + 1], minus = c > 0 ? f[i + 1] : f[i];
+                m[ax] = first ? plus : m[ax] + plus;
+                m[ax] = m[ax] - minus;
+                first = false;
+            }
+        }
+    }
+    rho = r;
+    ux = m[0] / r;
+    uy = m[1] / r;
+    uz = VS == ION_D2Q9 ? 0.0f / r : m[2] / r;
+}
+
+// calculate_f_eq, sim.cl:155-207 (DDF-shifted equilibrium)
+template <int VS> __device__ __forceinline__ void f_eq(float rho, float ux, float uy, float uz, float* feq) {
+    constexpr int QQ = VSet<VS>::Q;
+    const float c3 = -3.0f * (sq(ux) + sq(uy) + sq(uz)), rhom1 = rho - 1.0f;
+    ux *= 3.0f;
+    uy *= 3.0f;
+    uz *= 3.0f;
+    feq[0] = wclass<VS>(0) * fmaf(rho, 0.5f * c3, rhom1);
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        const float wi = wdir<VS>(i);
+        const float rhow = wi * rho, rhom1w = wi * rhom1;
+        const float ui = cdot<VS>(i, ux, uy, uz);
+        const float t = fmaf(ui, ui, c3);
+        feq[i] = fmaf(rhow, fmaf(0.5f, t, ui), rhom1w);
+        feq[i + 1] = fmaf(rhow, fmaf(0.5f, t, -ui), rhom1w);
+    }
+}
+
+// calculate_forcing_terms (Guo forcing), sim.cl:367-377
+template <int VS>
+__device__ __forceinline__ void forcing_terms(float ux, float uy, float uz, float fx, float fy, float fz, float* Fin) {
+    constexpr int QQ = VSet<VS>::Q;
+    const float uF = VS == ION_D2Q9 ? -0.33333334f * fmaf(ux, fx, uy * fy) : -0.33333334f * fmaf(ux, fx, fmaf(uy, fy, uz * fz));
+    Fin[0] = 9.0f * wclass<VS>(0) * uF;
+#pragma unroll
+    for (int i = 1; i < QQ; i++) {
+        Fin[i] = (9.0f * wdir<VS>(i)) * fmaf(cdot<VS>(i, fx, fy, fz), cdot<VS>(i, ux, uy, uz) + 0.33333334f, uF);
+    }
+}
+
+// calculate_a_eq (D3Q7 advected scalar), sim.cl:390-396
+__device__ __forceinline__ void a_eq(float Q, float ux, float uy, float uz, float* qeq) {
+    const float wsT4 = 0.5f * Q, wsTm1 = 0.125f * (Q - 1.0f);
+    qeq[0] = fmaf(0.25f, Q, -0.25f);
+    qeq[1] = fmaf(wsT4, ux, wsTm1); qeq[2] = fmaf(wsT4, -ux, wsTm1);
+    qeq[3] = fmaf(wsT4, uy, wsTm1); qeq[4] = fmaf(wsT4, -uy, wsTm1);
+    qeq[5] = fmaf(wsT4, uz, wsTm1); qeq[6] = fmaf(wsT4, -uz, wsTm1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// LOD pyramid helpers (sim.cl:425-447)
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lod_index(const KArgs& a, uint32_t x, uint32_t y, uint32_t z, uint32_t d) {
+    const uint32_t nd = 1u << d;
+    return x / (a.nx / nd) + (y / (a.ny / nd) + z / (a.nz / nd) * nd) * nd;
+}
+__device__ __forceinline__ float lod_s(const KArgs& a, uint32_t d) {
+    const uint32_t nd = 1u << d;
+    return (float)((a.nx / nd) * (a.ny / nd) * (a.nz / nd));
+}
+
+}  // namespace ion

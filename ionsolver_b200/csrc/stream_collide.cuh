@@ -1,0 +1,377 @@
+// stream_collide.cuh -- the fused hot kernel of the extended-LBM MHD time step, plus update_fields and
+// initialize, as templates over <velocity set, DDF storage type, MHD, TRT>.
+//
+// Behaviour follows /root/reference/src/kernels/sim_kernels.cl ("sim.cl"): stream_collide :465-758,
+// initialize :760-832, update_fields :834-859.  Design for B200 (sm_100a):
+//   * one thread per lattice cell, x fastest: every DDF access of a warp is one contiguous 128 B (FP32) /
+//     64 B (FP16) segment per direction -- the SoA layout i*N+n keeps all 2Q(+2Q+14) streams coalesced;
+//   * Esoteric-Pull in-place streaming: each (cell,slot) address is read and then written by the same
+//     thread, so no second DDF copy exists and algorithmic HBM traffic is the minimum 2*Q*s bytes/cell;
+//   * 3-D launch (x-chunk, y, z): no integer div/mod per cell, branch-free periodic wraps;
+//   * all loads of a cell (19+19+7 DDFs, E, B, flags) are issued before first use -> >50 independent
+//     requests in flight per thread, which is what saturates HBM3e at modest occupancy;
+//   * MHD source terms (electron-gas LBM, D3Q7 charge advection, Lorentz force) are applied in registers;
+//     the LOD deposit is a warp-segmented shuffle reduction followed by one red.global per (warp, LOD block)
+//     instead of the reference's 4 same-address atomics per cell (sim.cl:673-676);
+//   * EQUILIBRIUM_BOUNDARIES / VOLUME_FORCE / FORCE_FIELD / UPDATE_FIELDS are warp-uniform runtime switches
+//     (they do not change register pressure materially); Q, storage codec, MHD and TRT are compile time.
+// No tensor cores: the kernel is HBM-bound (153 B/cell plain, 389 B/cell MHD for D3Q19 FP32).
+#pragma once
+#include "lattice.cuh"
+
+namespace ion {
+
+constexpr int SC_BLOCK_MAX = 256;
+
+struct LodDeposit {
+    uint32_t ind;  // float index of the LOD entry (already *4), 0xFFFFFFFF = nothing to deposit
+    float q, ux, uy, uz;
+};
+
+// Warp-segmented reduction of LOD deposits: lanes of one warp are consecutive x cells, so equal LOD indices form
+// contiguous runs; each run is summed with shuffles and its head lane issues the 4 reductions.
+__device__ __forceinline__ void lod_deposit_warp(float* __restrict__ QU_lod, LodDeposit d) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t prev = __shfl_up_sync(full, d.ind, 1);
+    const bool head = (lane == 0u) || (prev != d.ind);
+    const unsigned heads = __ballot_sync(full, head);
+    const unsigned higher = lane == 31u ? 0u : (heads & ~((2u << lane) - 1u));
+    const int run_end = higher ? (__ffs(higher) - 1) : 32;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float oq = __shfl_down_sync(full, d.q, off);
+        const float ox = __shfl_down_sync(full, d.ux, off);
+        const float oy = __shfl_down_sync(full, d.uy, off);
+        const float oz = __shfl_down_sync(full, d.uz, off);
+        if ((int)lane + off < run_end) {
+            d.q += oq; d.ux += ox; d.uy += oy; d.uz += oz;
+        }
+    }
+    if (head && d.ind != 0xFFFFFFFFu) {
+        atomicAdd(&QU_lod[d.ind + 0], d.q);
+        atomicAdd(&QU_lod[d.ind + 1], d.ux);
+        atomicAdd(&QU_lod[d.ind + 2], d.uy);
+        atomicAdd(&QU_lod[d.ind + 3], d.uz);
+    }
+}
+
+template <int VS, int FP, bool MHD, bool TRT>
+__global__ void __launch_bounds__(SC_BLOCK_MAX)
+k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float fx, const float fy, const float fz) {
+    constexpr int QQ = VSet<VS>::Q;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    bool active = x < a.nx && !is_halo(a, x, y, z);  // sim.cl:485
+    const Cell c = make_cell(a, active ? x : 0u, y, z);
+    const uint32_t n = c.n;
+    uint8_t flagsn = 0;
+    if (active) {
+        flagsn = a.flags[n];
+        active = (flagsn & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:487-488 (quirk Q1: only exact TYPE_S is solid)
+    }
+    LodDeposit dep;
+    dep.ind = 0xFFFFFFFFu;
+    dep.q = dep.ux = dep.uy = dep.uz = 0.0f;
+    if (!MHD && !active) return;
+
+    if (active) {
+        const uint8_t bo = flagsn & ION_TYPE_BO;
+        const uint64_t N = a.N;
+        const uint64_t todd = t & 1ull;
+        const bool eqb = (a.ext & ION_EXT_EQUILIBRIUM_BOUNDARIES) != 0u;
+        const bool vf = (a.ext & ION_EXT_VOLUME_FORCE) != 0u;
+        const bool is_e = eqb && bo == ION_TYPE_E;
+        auto nb = [&](int i) { return neighbor<VS>(c, i); };
+
+        float fhn[QQ];
+        ep_load<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 2, sim.cl:494
+
+        // ---- issue the MHD loads early so that they overlap with the gas moments ----
+        float ehn[MHD ? QQ : 1];
+        float qhn[7];
+        float Bx = 0.f, By = 0.f, Bz = 0.f, Ex = 0.f, Ey = 0.f, Ez = 0.f;
+        if (MHD) {
+            Bx = a.B_dyn[n]; By = a.B_dyn[N + n]; Bz = a.B_dyn[2ull * N + n];  // sim.cl:532-533
+            Ex = a.E_dyn[n]; Ey = a.E_dyn[N + n]; Ez = a.E_dyn[2ull * N + n];
+            ep_load<FP, QQ>(ehn, a.ei, N, n, todd, nb);                         // sim.cl:538
+            ep_load<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
+        }
+
+        float rhon, uxn, uyn, uzn;
+        if (is_e) {  // sim.cl:503-507
+            rhon = a.rho[n];
+            uxn = a.u[n];
+            uyn = a.u[N + n];
+            uzn = a.u[2ull * N + n];
+        } else {
+            rho_u<VS>(fhn, rhon, uxn, uyn, uzn);
+        }
+
+        float fxn = fx, fyn = fy, fzn = fz;  // sim.cl:513
+        float Fin[QQ], feq[QQ];
+        const float w = a.w;
+        const float c_tau = fmaf(w, -0.5f, 1.0f);  // sim.cl:519
+        if (a.ext & ION_EXT_FORCE_FIELD) {          // sim.cl:522-528
+            fxn += a.F[n];
+            fyn += a.F[N + n];
+            fzn += a.F[2ull * N + n];
+        }
+
+        if (MHD) {
+            // electron gas part 1, sim.cl:537-540
+            float rhon_e, uxn_e, uyn_e, uzn_e;
+            rho_u<VS>(ehn, rhon_e, uxn_e, uyn_e, uzn_e);
+            // gas charge advection 1, sim.cl:551-553
+            float rhon_q = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 7; i++) rhon_q += qhn[i];
+            rhon_q += 1.0f;
+            // gas charge advection 2, sim.cl:633-637
+            a.Q[n] = rhon_q - rhon_e;
+            {
+                float qeq[7];
+                a_eq(rhon_q, uxn, uyn, uzn, qeq);
+                const float wq = a.wq;
+#pragma unroll
+                for (int i = 0; i < 7; i++) qhn[i] = fmaf(1.0f - wq, qhn[i], wq * qeq[i]);
+                ep_store<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });
+            }
+            // electron gas part 2, sim.cl:641-656
+            const float nre = -rhon_e;
+            const float efx = nre * (Ex + (uyn_e * Bz - uzn_e * By));
+            const float efy = nre * (Ey + (uzn_e * Bx - uxn_e * Bz));
+            const float efz = nre * (Ez + (uxn_e * By - uyn_e * Bx));
+            const float rho2_e = 0.5f / (rhon_e * a.kkge);
+            uxn_e = clampf(fmaf(efx, rho2_e, uxn_e), -ION_DEF_C, ION_DEF_C);
+            uyn_e = clampf(fmaf(efy, rho2_e, uyn_e), -ION_DEF_C, ION_DEF_C);
+            uzn_e = clampf(fmaf(efz, rho2_e, uzn_e), -ION_DEF_C, ION_DEF_C);
+            forcing_terms<VS>(uxn_e, uyn_e, uzn_e, efx, efy, efz, Fin);
+            f_eq<VS>(rhon_e, uxn_e, uyn_e, uzn_e, feq);
+#pragma unroll
+            for (int i = 0; i < QQ; i++) {
+                const float Fi = Fin[i] * c_tau;
+                ehn[i] = is_e ? feq[i] : fmaf(1.0f - w, ehn[i], fmaf(w, feq[i], Fi));  // always SRT, sim.cl:649-655
+            }
+            ep_store<FP, QQ>(ehn, a.ei, N, n, todd, nb);
+            // EM force on gas (pre-force gas velocity), sim.cl:660-662
+            fxn += rhon_q * (Ex + uyn * Bz - uzn * By);
+            fyn += rhon_q * (Ey + uzn * Bx - uxn * Bz);
+            fzn += rhon_q * (Ez + uxn * By - uyn * Bx);
+            // LOD construction, sim.cl:666-677
+            if (a.lod_depth > 0u) {
+                uint32_t off = 0u;
+                if (a.dx > 1u || a.dy > 1u || a.dz > 1u) {
+                    for (uint32_t d = 0u; d < a.lod_depth; d++) off += 1u << (d * (uint32_t)VSet<VS>::DIM);
+                }
+                dep.ind = (lod_index(a, x, y, z, a.lod_depth) + off) * 4u;
+                const float ils = 1.0f / lod_s(a, a.lod_depth);
+                dep.q = rhon_q - rhon_e;
+                dep.ux = uxn * ils;
+                dep.uy = uyn * ils;
+                dep.uz = uzn * ils;
+            }
+        }
+
+        if (vf) {  // sim.cl:680-685
+            const float rho2 = 0.5f / rhon;
+            uxn = clampf(fmaf(fxn, rho2, uxn), -ION_DEF_C, ION_DEF_C);
+            uyn = clampf(fmaf(fyn, rho2, uyn), -ION_DEF_C, ION_DEF_C);
+            uzn = clampf(fmaf(fzn, rho2, uzn), -ION_DEF_C, ION_DEF_C);
+            forcing_terms<VS>(uxn, uyn, uzn, fxn, fyn, fzn, Fin);
+        } else {  // sim.cl:687-690
+            uxn = clampf(uxn, -ION_DEF_C, ION_DEF_C);
+            uyn = clampf(uyn, -ION_DEF_C, ION_DEF_C);
+            uzn = clampf(uzn, -ION_DEF_C, ION_DEF_C);
+#pragma unroll
+            for (int i = 0; i < QQ; i++) Fin[i] = 0.0f;
+        }
+
+        if ((a.ext & ION_EXT_UPDATE_FIELDS) && !is_e) {  // sim.cl:694-710
+            a.rho[n] = rhon;
+            a.u[n] = uxn;
+            a.u[N + n] = uyn;
+            a.u[2ull * N + n] = uzn;
+        }
+
+        f_eq<VS>(rhon, uxn, uyn, uzn, feq);  // sim.cl:712
+
+        if (!TRT) {  // sim.cl:714-723
+#pragma unroll
+            for (int i = 0; i < QQ; i++) {
+                const float Fi = vf ? Fin[i] * c_tau : Fin[i];
+                fhn[i] = is_e ? feq[i] : fmaf(1.0f - w, fhn[i], fmaf(w, feq[i], Fi));
+            }
+        } else {  // sim.cl:725-755
+            const float wp = w;
+            const float wm = 1.0f / (0.1875f / (1.0f / w - 0.5f) + 0.5f);
+            if (vf) {
+                const float c_taup = fmaf(wp, -0.25f, 0.5f), c_taum = fmaf(wm, -0.25f, 0.5f);
+                float Fib[QQ];
+                Fib[0] = Fin[0];
+#pragma unroll
+                for (int i = 1; i < QQ; i += 2) {
+                    Fib[i] = Fin[i + 1];
+                    Fib[i + 1] = Fin[i];
+                }
+#pragma unroll
+                for (int i = 0; i < QQ; i++) Fin[i] = fmaf(c_taup, Fin[i] + Fib[i], c_taum * (Fin[i] - Fib[i]));
+            }
+            float fhb[QQ], feb[QQ];
+            fhb[0] = fhn[0];
+            feb[0] = feq[0];
+#pragma unroll
+            for (int i = 1; i < QQ; i += 2) {
+                fhb[i] = fhn[i + 1];
+                fhb[i + 1] = fhn[i];
+                feb[i] = feq[i + 1];
+                feb[i + 1] = feq[i];
+            }
+#pragma unroll
+            for (int i = 0; i < QQ; i++) {
+                fhn[i] = is_e ? feq[i]
+                              : fmaf(0.5f * wp, feq[i] - fhn[i] + feb[i] - fhb[i],
+                                     fmaf(0.5f * wm, feq[i] - feb[i] - fhn[i] + fhb[i], fhn[i] + Fin[i]));
+            }
+        }
+        ep_store<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 1, sim.cl:757
+    }
+
+    if (MHD) lod_deposit_warp(a.QU_lod, dep);
+}
+
+// update_fields, sim.cl:834-859
+template <int VS, int FP>
+__global__ void __launch_bounds__(SC_BLOCK_MAX) k_update_fields(const __grid_constant__ KArgs a, const uint64_t t) {
+    constexpr int QQ = VSet<VS>::Q;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= a.nx || is_halo(a, x, y, z)) return;
+    const Cell c = make_cell(a, x, y, z);
+    const uint32_t n = c.n;
+    if ((a.flags[n] & ION_TYPE_BO) == ION_TYPE_S) return;
+    float fhn[QQ];
+    ep_load<FP, QQ>(fhn, a.fi, a.N, n, t & 1ull, [&](int i) { return neighbor<VS>(c, i); });
+    float rhon, uxn, uyn, uzn;
+    rho_u<VS>(fhn, rhon, uxn, uyn, uzn);
+    a.rho[n] = rhon;
+    a.u[n] = clampf(uxn, -ION_DEF_C, ION_DEF_C);
+    a.u[a.N + n] = clampf(uyn, -ION_DEF_C, ION_DEF_C);
+    a.u[2ull * a.N + n] = clampf(uzn, -ION_DEF_C, ION_DEF_C);
+}
+
+// initialize, sim.cl:760-832.  The neighbour-flag scan of sim.cl:782-794 has no effect on the result (the
+// inner `flagsn_bo==TYPE_S` test at :795 is always true inside the solid branch), so flags of neighbours are
+// not read here; the visible end state is identical.
+template <int VS, int FP, bool MHD>
+__global__ void __launch_bounds__(SC_BLOCK_MAX) k_initialize(const __grid_constant__ KArgs a) {
+    constexpr int QQ = VSet<VS>::Q;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= a.nx || is_halo(a, x, y, z)) return;
+    const Cell c = make_cell(a, x, y, z);
+    const uint32_t n = c.n;
+    const uint64_t N = a.N;
+    const uint8_t bo = a.flags[n] & ION_TYPE_BO;
+    float ux = a.u[n], uy = a.u[N + n], uz = a.u[2ull * N + n];
+    float Qn = MHD ? a.Q[n] : 0.0f;
+    if (bo == ION_TYPE_S) {  // sim.cl:784-803
+        ux = uy = uz = 0.0f;
+        a.u[n] = 0.0f;
+        a.u[N + n] = 0.0f;
+        a.u[2ull * N + n] = 0.0f;
+        if (MHD) {
+            Qn = 0.0f;
+            a.Q[n] = 0.0f;
+        }
+    }
+    auto nb = [&](int i) { return neighbor<VS>(c, i); };
+    float feq[QQ];
+    f_eq<VS>(a.rho[n], ux, uy, uz, feq);
+    ep_store<FP, QQ>(feq, a.fi, N, n, 1ull, nb);  // sim.cl:806
+    if (MHD) {
+        float qeq[7];
+        a_eq(Qn, ux, uy, uz, qeq);  // sim.cl:811-814
+        auto nb7 = [&](int i) { return neighbor7(c, i); };
+        ep_store<FP, 7>(qeq, a.fqi, N, n, 1ull, nb7);
+        a.B_dyn[n] = a.B_stat[n];  // sim.cl:816-821
+        a.B_dyn[N + n] = a.B_stat[N + n];
+        a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n];
+        a.E_dyn[n] = a.E_stat[n];
+        a.E_dyn[N + n] = a.E_stat[N + n];
+        a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n];
+        f_eq<VS>(0.0f, ux, uy, uz, feq);  // sim.cl:823-825 (quirk Q10: electron gas starts at rho_e = 0)
+        ep_store<FP, QQ>(feq, a.ei, N, n, 1ull, nb);
+        if (a.ext & ION_EXT_SUBGRID_ECR) {  // sim.cl:827-831
+            a_eq(a.Et[n], ux, uy, uz, qeq);
+            ep_store<FP, 7>(qeq, a.eti, N, n, 1ull, nb7);
+        }
+    }
+}
+
+inline dim3 cell_grid(const KArgs& a, unsigned& block) {
+    unsigned b = ((a.nx + 31u) / 32u) * 32u;
+    if (b > (unsigned)SC_BLOCK_MAX) b = SC_BLOCK_MAX;
+    block = b;
+    return dim3((a.nx + b - 1u) / b, a.ny, a.nz);
+}
+
+// per-velocity-set launchers (one translation unit each, see sc_d*.cu)
+template <int VS>
+cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx, float fy, float fz,
+                                     cudaStream_t s);
+template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
+template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
+
+#define ION_SC_CASE(FPV, MHDV, TRTV)                                                                   \
+    if (fp == FPV && mhd == MHDV && trt == TRTV) {                                                     \
+        k_stream_collide<VS, FPV, MHDV, TRTV><<<grid, block, 0, s>>>(a, t, fx, fy, fz);                \
+        return cudaGetLastError();                                                                     \
+    }
+
+#define ION_DEFINE_VS_LAUNCHERS(VSV, ALLOW_MHD)                                                                      \
+    template <>                                                                                                      \
+    cudaError_t launch_stream_collide_vs<VSV>(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx,      \
+                                              float fy, float fz, cudaStream_t s) {                                  \
+        constexpr int VS = VSV;                                                                                      \
+        unsigned block;                                                                                              \
+        const dim3 grid = cell_grid(a, block);                                                                       \
+        ION_SC_CASE(ION_FP32, false, false)                                                                          \
+        ION_SC_CASE(ION_FP32, false, true)                                                                           \
+        ION_SC_CASE(ION_FP16S, false, false)                                                                         \
+        ION_SC_CASE(ION_FP16S, false, true)                                                                          \
+        ION_SC_CASE(ION_FP16C, false, false)                                                                         \
+        ION_SC_CASE(ION_FP16C, false, true)                                                                          \
+        if (ALLOW_MHD) {                                                                                             \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, false)                                                            \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, true)                                                             \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, false)                                                           \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, true)                                                            \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, false)                                                           \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, true)                                                            \
+        }                                                                                                            \
+        return cudaErrorInvalidValue;                                                                                \
+    }                                                                                                                \
+    template <> cudaError_t launch_update_fields_vs<VSV>(const KArgs& a, int fp, uint64_t t, cudaStream_t s) {       \
+        unsigned block;                                                                                              \
+        const dim3 grid = cell_grid(a, block);                                                                       \
+        if (fp == ION_FP32) k_update_fields<VSV, ION_FP32><<<grid, block, 0, s>>>(a, t);                             \
+        else if (fp == ION_FP16S) k_update_fields<VSV, ION_FP16S><<<grid, block, 0, s>>>(a, t);                      \
+        else k_update_fields<VSV, ION_FP16C><<<grid, block, 0, s>>>(a, t);                                           \
+        return cudaGetLastError();                                                                                   \
+    }                                                                                                                \
+    template <> cudaError_t launch_initialize_vs<VSV>(const KArgs& a, int fp, bool mhd, cudaStream_t s) {            \
+        unsigned block;                                                                                              \
+        const dim3 grid = cell_grid(a, block);                                                                       \
+        if (!mhd) {                                                                                                  \
+            if (fp == ION_FP32) k_initialize<VSV, ION_FP32, false><<<grid, block, 0, s>>>(a);                        \
+            else if (fp == ION_FP16S) k_initialize<VSV, ION_FP16S, false><<<grid, block, 0, s>>>(a);                 \
+            else k_initialize<VSV, ION_FP16C, false><<<grid, block, 0, s>>>(a);                                      \
+        } else if (ALLOW_MHD) {                                                                                      \
+            if (fp == ION_FP32) k_initialize<VSV, ION_FP32, (bool)ALLOW_MHD><<<grid, block, 0, s>>>(a);              \
+            else if (fp == ION_FP16S) k_initialize<VSV, ION_FP16S, (bool)ALLOW_MHD><<<grid, block, 0, s>>>(a);       \
+            else k_initialize<VSV, ION_FP16C, (bool)ALLOW_MHD><<<grid, block, 0, s>>>(a);                            \
+        } else {                                                                                                     \
+            return cudaErrorInvalidValue;                                                                            \
+        }                                                                                                            \
+        return cudaGetLastError();                                                                                   \
+    }
+
+}  // namespace ion
