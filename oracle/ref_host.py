@@ -305,11 +305,8 @@ class RefDomain:
         from . import build_ref
         self.cfg = cfg
         self.g = g = domain_geometry(cfg, x, y, z, i)
-        self.lib_path = lib_path or build_ref.build(cfg, g)
-        self.lib = ctypes.CDLL(self.lib_path)
-        self._declare()
-        if threads:
-            self.lib.ref_set_threads(threads)
+        self.threads = threads
+        self._load(lib_path)
         dim, q, transfers = SET_VALUES[cfg.velocity_set]
         self.q, self.transfers = q, transfers
         n = g.n
@@ -349,6 +346,14 @@ class RefDomain:
         self.transfer_p = np.zeros(max(tsize, 1), np.uint8)
         self.transfer_m = np.zeros(max(tsize, 1), np.uint8)
         self.transfer_lod_host = np.zeros(4 * g.n_lod_own, np.float32) if mhd else None
+
+    def _load(self, lib_path=None):
+        from . import build_ref
+        self.lib_path = lib_path or build_ref.build(self.cfg, self.g)
+        self.lib = ctypes.CDLL(self.lib_path)
+        self._declare()
+        if self.threads:
+            self.lib.ref_set_threads(self.threads)
 
     def _declare(self):
         L, c = self.lib, ctypes
@@ -453,9 +458,28 @@ class RefDomain:
                 mpc = [u.magnetization_si_lu(v) for v in value]
             elif ctype in ("Charged", "ChargedECR"):
                 mpc[0] = u.charge_si_lu(value)
+        self._voxelize(direction, flag, mpc)
+        return direction, flag, mpc
+
+    # probes
+    def codec(self, arr, direction):  # 0: float -> stored, 1: stored -> float
+        if direction == 0:
+            a = np.ascontiguousarray(arr, np.float32)
+            out = np.empty(a.size, np.float32 if self.cfg.float_type == "FP32" else np.uint16)
+        else:
+            a = np.ascontiguousarray(arr)
+            out = np.empty(a.size, np.float32)
+        self.lib.ref_codec(a.ctypes.data, out.ctypes.data, a.size, direction)
+        return out
+
+    def neighbors(self, n):
+        j = np.zeros(self.q, np.uint32)
+        self.lib.ref_neighbors(int(n), j.ctypes.data)
+        return j
+
+    def _voxelize(self, direction, flag, mpc):
         self.lib.ref_voxelize_mesh(self.bufs(), direction, self.t + 1, flag, mpc[0], mpc[1], mpc[2],
                                    self.get_area(direction))
-        return direction, flag, mpc
 
 
 class Mesh:
@@ -551,7 +575,9 @@ class Mesh:
 class RefLbm:
     """Lbm (mod.rs:152-495) over RefDomain objects."""
 
-    def __init__(self, cfg: RefConfig, threads=0):
+    def __init__(self, cfg: RefConfig, threads=0, backend="ref"):
+        """backend "ref": the reference's own kernel source compiled for the host (oracle/_ref);
+        backend "port": the plain-C restatement (oracle/lbm_oracle.c)."""
         cfg = dataclasses.replace(cfg)
         cfg.n_x = (cfg.n_x // cfg.d_x) * cfg.d_x  # mod.rs:167-179
         cfg.n_y = (cfg.n_y // cfg.d_y) * cfg.d_y
@@ -560,7 +586,11 @@ class RefLbm:
         self.domains = []
         for d in range(cfg.d_x * cfg.d_y * cfg.d_z):
             x, y, z = domain_coords(d, cfg.d_x, cfg.d_y)
-            self.domains.append(RefDomain(cfg, x, y, z, d, threads=threads))
+            if backend == "port":
+                from .port import PortDomain
+                self.domains.append(PortDomain(cfg, x, y, z, d, threads=threads))
+            else:
+                self.domains.append(RefDomain(cfg, x, y, z, d, threads=threads))
         self.meshes = []
         self.initialized = False
 
