@@ -160,6 +160,33 @@ ION_API int ion_enqueue_precompute_e_ecr(ion_domain_t* dom); /* domain.rs:569-57
 ION_API int ion_domain_set_ecr_freq(ion_domain_t* dom, float ecrf); /* kernel arg "ecrf", domain.rs:292-296 */
 ION_API int ion_finish(ion_domain_t* dom);                   /* queue.finish(), mod.rs:275-279 */
 
+/* halo exchange ---------------------------------------------------------------------------------------------
+ * The reference stages every face through host memory and swaps the two host vectors of neighbouring domains
+ * (std::ptr::swap of transfer_p_host / transfer_m_host, src/lbm/mod.rs:380-384, around the buffer reads/writes of
+ * src/lbm/domain.rs:504-531).  Here the faces never leave device memory:
+ *   ion_exchange_transfer   one process, two domains: d's transfer_p <-> dp's transfer_m.  Same device: the two
+ *                           device pointers are swapped (zero copy, ordered with events); different devices: peer
+ *                           copies over NVLink into the partner's spare buffer, then the spare becomes current.
+ *   ion_comm_*              one process per GPU (the layout bench.py / torchrun uses): NCCL point-to-point over
+ *                           NVLink between ring neighbours, and an all-gather for the LOD pyramids.
+ * `bytes` is the face payload (area * bytes_per_cell of mod.rs:410-433); the packed [b*A+a] layout is untouched. */
+ION_API int ion_exchange_transfer(ion_domain_t* d, ion_domain_t* dp, size_t bytes);
+/* single-process LOD exchange (Lbm::communicate_qu_lods, mod.rs:436-468): copies own-pyramid entries
+ * [src_entry, src_entry+entries) of `src` to entry `dst_entry` of `dst` (entries are 4 floats) */
+ION_API int ion_copy_lods(ion_domain_t* dst, uint32_t dst_entry, ion_domain_t* src, uint32_t src_entry, uint32_t entries);
+
+typedef struct ion_comm ion_comm_t;
+#define ION_COMM_ID_BYTES 128
+ION_API int ion_comm_unique_id(uint8_t id[ION_COMM_ID_BYTES]); /* rank 0 creates, the launcher broadcasts (torch.distributed) */
+ION_API int ion_comm_create(const uint8_t id[ION_COMM_ID_BYTES], int rank, int world, int device, ion_comm_t** out);
+ION_API int ion_comm_destroy(ion_comm_t* comm);
+/* the p<->m swap with ring neighbours that live in other processes: sends this domain's transfer_p to `rank_p`
+ * (where it becomes transfer_m) and transfer_m to `rank_m` (becomes transfer_p), receives the mirror images */
+ION_API int ion_comm_exchange_transfer(ion_comm_t* comm, ion_domain_t* d, int rank_p, int rank_m, size_t bytes);
+/* all ranks' own LOD pyramids (n_lod_own entries each) gathered into `d`'s scratch, then the level every foreign
+ * domain contributes (mod.rs:448-465) is copied into QU_lod after n_lod_own, ascending domain index */
+ION_API int ion_comm_exchange_lods(ion_comm_t* comm, ion_domain_t* d);
+
 /* instrumentation (no reference equivalent): kernels launched by this library since load, for bench.py */
 ION_API uint64_t ion_kernel_launch_count(void);
 /* the CUDA stream of a domain (cudaStream_t as void*), so callers can record CUDA events on it */

@@ -45,7 +45,22 @@ SYMBOLS = [
     "ion_enqueue_transfer_extract", "ion_enqueue_transfer_insert", "ion_voxelize_mesh", "ion_enqueue_precompute_b",
     "ion_enqueue_precompute_e", "ion_enqueue_precompute_e_ecr", "ion_domain_set_ecr_freq", "ion_finish",
     "ion_kernel_launch_count", "ion_domain_stream",
+    "ion_exchange_transfer", "ion_copy_lods", "ion_comm_unique_id", "ion_comm_create", "ion_comm_destroy",
+    "ion_comm_exchange_transfer", "ion_comm_exchange_lods",
 ]
+# every symbol include/ionsolver_b200_host.h declares
+HOST_SYMBOLS = [
+    "ion_lbm_config_default", "ion_units_set", "ion_units_eval", "ion_lbm_make_params", "ion_lbm_create",
+    "ion_lbm_create_distributed", "ion_lbm_destroy", "ion_lbm_get_config", "ion_lbm_local_domains", "ion_lbm_domain",
+    "ion_lbm_initialize", "ion_lbm_run", "ion_lbm_do_time_step", "ion_lbm_finish_queues", "ion_lbm_get_time_step",
+    "ion_lbm_precompute_b", "ion_lbm_precompute_e", "ion_lbm_precompute_e_ecr", "ion_lbm_communicate_field",
+    "ion_lbm_communicate_qu_lods", "ion_lbm_set_time_step", "ion_lbm_import_mesh", "ion_lbm_import_mesh_reposition",
+    "ion_lbm_voxelise_mesh", "ion_lbm_mesh_info", "ion_lbm_mesh_triangles", "ion_lbm_mesh_translate",
+    "ion_lbm_set_taylor_green", "ion_lbm_setup_velocity_field", "ion_setup_taylor_green", "ion_setup_lid_driven_cavity",
+    "ion_setup_charged_fluid", "ion_lbm_encode", "ion_lbm_decode", "ion_lbm_write_file", "ion_lbm_read_file",
+    "ion_config_to_json", "ion_config_from_json", "ion_lbm_dump_cell", "ion_free",
+]
+COMM_ID_BYTES = 128
 
 
 class IonParams(ctypes.Structure):
@@ -63,6 +78,25 @@ class IonParams(ctypes.Structure):
         ("wq", ctypes.c_float),
         ("kkbme", ctypes.c_float), ("keabs", ctypes.c_float),
         ("lod_depth", ctypes.c_uint32), ("n_lod", ctypes.c_uint32), ("n_lod_own", ctypes.c_uint32),
+    ]
+
+
+class IonLbmConfig(ctypes.Structure):
+    """IonLbmConfig of include/ionsolver_b200_host.h (LbmConfig + Units, mod.rs:46-101, units.rs:14-27)."""
+    _fields_ = [
+        ("velocity_set", ctypes.c_uint32), ("relaxation_time", ctypes.c_uint32), ("float_type", ctypes.c_uint32),
+        ("unit_m", ctypes.c_float), ("unit_kg", ctypes.c_float), ("unit_s", ctypes.c_float), ("unit_a", ctypes.c_float),
+        ("unit_k", ctypes.c_float),
+        ("propellant", ctypes.c_uint32),
+        ("n_x", ctypes.c_uint32), ("n_y", ctypes.c_uint32), ("n_z", ctypes.c_uint32),
+        ("d_x", ctypes.c_uint32), ("d_y", ctypes.c_uint32), ("d_z", ctypes.c_uint32),
+        ("nu", ctypes.c_float),
+        ("f_x", ctypes.c_float), ("f_y", ctypes.c_float), ("f_z", ctypes.c_float),
+        ("ext_equilibrium_boudaries", ctypes.c_uint8), ("ext_volume_force", ctypes.c_uint8),
+        ("ext_force_field", ctypes.c_uint8), ("ext_magneto_hydro", ctypes.c_uint8), ("ext_subgrid_ecr", ctypes.c_uint8),
+        ("mhd_lod_depth", ctypes.c_uint8), ("graphics_active", ctypes.c_uint8), ("reserved", ctypes.c_uint8),
+        ("ecr_freq", ctypes.c_float), ("ecr_field_strength", ctypes.c_float),
+        ("run_steps", ctypes.c_uint64),
     ]
 
 
@@ -114,6 +148,58 @@ def load() -> ctypes.CDLL:
     L.ion_finish.argtypes = [D]
     L.ion_kernel_launch_count.restype = c.c_uint64
     L.ion_domain_stream.argtypes = [D, c.POINTER(c.c_void_p)]
+    L.ion_exchange_transfer.argtypes = [D, D, c.c_size_t]
+    L.ion_copy_lods.argtypes = [D, c.c_uint32, D, c.c_uint32, c.c_uint32]
+    L.ion_comm_unique_id.argtypes = [c.c_void_p]
+    L.ion_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_int, c.POINTER(c.c_void_p)]
+    L.ion_comm_destroy.argtypes = [c.c_void_p]
+    L.ion_comm_exchange_transfer.argtypes = [c.c_void_p, D, c.c_int, c.c_int, c.c_size_t]
+    L.ion_comm_exchange_lods.argtypes = [c.c_void_p, D]
+    # ---- host layer (include/ionsolver_b200_host.h) ----
+    CFG = c.POINTER(IonLbmConfig)
+    H = c.c_void_p
+    PI = c.POINTER(c.c_int)
+    L.ion_lbm_config_default.argtypes = [CFG]
+    L.ion_lbm_config_default.restype = None
+    L.ion_units_set.argtypes = [CFG] + [c.c_float] * 10
+    L.ion_units_set.restype = None
+    L.ion_units_eval.argtypes = [CFG, c.c_int, c.c_float]
+    L.ion_units_eval.restype = c.c_float
+    L.ion_lbm_make_params.argtypes = [CFG, c.c_uint32, c.POINTER(IonParams)]
+    L.ion_lbm_create.argtypes = [CFG, PI, c.c_int, c.POINTER(H)]
+    L.ion_lbm_create_distributed.argtypes = [CFG, c.c_int, c.c_int, c.c_int, c.c_void_p, c.POINTER(H)]
+    L.ion_lbm_destroy.argtypes = [H]
+    L.ion_lbm_get_config.argtypes = [H, CFG]
+    L.ion_lbm_local_domains.argtypes = [H, c.POINTER(c.c_uint32)]
+    L.ion_lbm_domain.argtypes = [H, c.c_uint32, c.POINTER(D), c.POINTER(c.c_uint32)]
+    for n in ("ion_lbm_initialize", "ion_lbm_do_time_step", "ion_lbm_finish_queues", "ion_lbm_precompute_b",
+              "ion_lbm_precompute_e", "ion_lbm_precompute_e_ecr", "ion_lbm_communicate_qu_lods"):
+        getattr(L, n).argtypes = [H]
+    L.ion_lbm_run.argtypes = [H, c.c_uint64]
+    L.ion_lbm_get_time_step.argtypes = [H, c.POINTER(c.c_uint64)]
+    L.ion_lbm_set_time_step.argtypes = [H, c.c_uint64]
+    L.ion_lbm_communicate_field.argtypes = [H, c.c_int]
+    L.ion_lbm_import_mesh.argtypes = [H, c.c_char_p] + [c.c_float] * 7
+    L.ion_lbm_import_mesh_reposition.argtypes = [H, c.c_char_p] + [c.c_float] * 7
+    L.ion_lbm_voxelise_mesh.argtypes = [H, c.c_uint32, c.c_int, c.c_float, c.c_float, c.c_float]
+    L.ion_lbm_mesh_info.argtypes = [H, c.c_uint32, c.POINTER(c.c_uint32), c.c_void_p, c.c_void_p]
+    L.ion_lbm_mesh_triangles.argtypes = [H, c.c_uint32, c.c_void_p, c.c_void_p, c.c_void_p]
+    L.ion_lbm_mesh_translate.argtypes = [H, c.c_uint32, c.c_float, c.c_float, c.c_float]
+    L.ion_lbm_set_taylor_green.argtypes = [H, c.c_uint32]
+    L.ion_lbm_setup_velocity_field.argtypes = [H, c.c_float, c.c_float, c.c_float, c.c_float]
+    L.ion_setup_taylor_green.argtypes = [c.c_uint32, c.c_uint32, c.c_int, c.c_int, c.c_int, PI, c.c_int, c.POINTER(H)]
+    L.ion_setup_lid_driven_cavity.argtypes = [c.c_uint32, PI, c.c_int, c.POINTER(H)]
+    L.ion_setup_charged_fluid.argtypes = [c.c_uint32, c.c_uint32, c.c_uint32, c.c_int, c.c_int, c.c_uint32, c.c_char_p, PI,
+                                          c.c_int, c.POINTER(H)]
+    L.ion_lbm_encode.argtypes = [H, c.c_int, c.POINTER(c.c_void_p), c.POINTER(c.c_size_t)]
+    L.ion_lbm_decode.argtypes = [c.c_void_p, c.c_size_t, CFG, c.c_int, PI, c.c_int, c.POINTER(H)]
+    L.ion_lbm_write_file.argtypes = [H, c.c_char_p]
+    L.ion_lbm_read_file.argtypes = [c.c_char_p, CFG, c.POINTER(H)]
+    L.ion_config_to_json.argtypes = [CFG, c.POINTER(c.c_void_p)]
+    L.ion_config_from_json.argtypes = [c.c_char_p, CFG]
+    L.ion_lbm_dump_cell.argtypes = [H, c.c_uint32, c.c_uint64, c.POINTER(c.c_void_p)]
+    L.ion_free.argtypes = [c.c_void_p]
+    L.ion_free.restype = None
     _lib = L
     return L
 
@@ -136,16 +222,24 @@ def kernel_launch_count() -> int:
 class Domain:
     """Thin RAII wrapper around ion_domain_t* with numpy-based buffer access."""
 
-    def __init__(self, params: IonParams, device: int = 0):
+    def __init__(self, params: IonParams = None, device: int = 0, borrowed=None):
         self.lib = load()
-        self.params = params
-        self.handle = ctypes.c_void_p()
-        check(self.lib.ion_domain_create(ctypes.byref(params), device, ctypes.byref(self.handle)))
-        self.ddf_dtype = np.float32 if params.float_type == FP32 else np.uint16
+        self.owned = borrowed is None
+        if borrowed is None:
+            self.params = params
+            self.handle = ctypes.c_void_p()
+            check(self.lib.ion_domain_create(ctypes.byref(params), device, ctypes.byref(self.handle)))
+        else:  # &lbm.domains[i]: owned by the Lbm
+            self.handle = borrowed
+            self.params = IonParams()
+            check(self.lib.ion_domain_params(self.handle, ctypes.byref(self.params)))
+        self.ddf_dtype = np.float32 if self.params.float_type == FP32 else np.uint16
+        self.n = self.params.nx * self.params.ny * self.params.nz
 
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
-            self.lib.ion_domain_destroy(self.handle)
+            if self.owned:
+                self.lib.ion_domain_destroy(self.handle)
             self.handle = ctypes.c_void_p()
 
     def __del__(self):

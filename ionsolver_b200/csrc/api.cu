@@ -9,7 +9,7 @@
 #include <cstring>
 #include <new>
 
-#include "lattice.cuh"
+#include "domain_internal.cuh"
 
 namespace ion {
 // launchers implemented in the kernel translation units
@@ -40,37 +40,25 @@ __global__ void k_fill_f32(float* p, uint64_t n, float v) {
 
 using namespace ion;
 
-struct ion_domain {
-    IonParams params;
-    int device;
-    cudaStream_t stream;
-    void* buf[ION_FIELD_COUNT];
-    size_t bytes[ION_FIELD_COUNT];
-    KArgs k;
-    void* lod_sources;   // scratch of update_e_b_dynamic
-    uint32_t* cp_counts; // scratch of the precompute compaction
-    float ecrf;
-};
-
 static thread_local char g_err[512] = "";
-static std::atomic<uint64_t> g_launches{0};
-
-static int fail(int code, const char* fmt, ...) {
+namespace ion {
+std::atomic<uint64_t> g_launches{0};
+int fail(int code, const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
     return code;
 }
-static int cuda_fail(cudaError_t e, const char* what) {
+int cuda_fail(cudaError_t e, const char* what) {
     snprintf(g_err, sizeof(g_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     return (int)e;
 }
-#define ION_CUDA(call)                                        \
-    do {                                                      \
-        cudaError_t ion_e_ = (call);                          \
-        if (ion_e_ != cudaSuccess) return cuda_fail(ion_e_, #call); \
-    } while (0)
+void set_transfer_ptrs(ion_domain* d) {
+    d->k.transfer_p = (uint8_t*)d->buf[ION_FIELD_TRANSFER_P];
+    d->k.transfer_m = (uint8_t*)d->buf[ION_FIELD_TRANSFER_M];
+}
+}  // namespace ion
 
 static int set_q(int vs, int* q, int* dim, int* tr) {
     switch (vs) {
@@ -171,6 +159,13 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
     }
     k_fill_f32<<<(unsigned)((n + 255) / 256), 256, 0, d->stream>>>((float*)d->buf[ION_FIELD_RHO], n, 1.0f);  // rho = 1, domain.rs:156
     g_launches++;
+    if (a_max) {  // spare face buffers: receive side of the device-resident halo exchange
+        e = cudaMalloc(&d->alt_p, B[ION_FIELD_TRANSFER_P]);
+        if (e == cudaSuccess) e = cudaMalloc(&d->alt_m, B[ION_FIELD_TRANSFER_M]);
+        if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc spare transfer buffers"); }
+    }
+    e = cudaEventCreateWithFlags(&d->ev, cudaEventDisableTiming);
+    if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaEventCreate"); }
     if (mhd) {
         e = cudaMalloc(&d->lod_sources, lod_source_bytes(p->lod_depth, p->n_lod_own, p->dx, p->dy, p->dz, p->di));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d->cp_counts, compaction_scratch_bytes(n));
@@ -220,6 +215,10 @@ int ion_domain_destroy(ion_domain_t* d) {
         if (d->buf[f]) cudaFree(d->buf[f]);
     if (d->lod_sources) cudaFree(d->lod_sources);
     if (d->cp_counts) cudaFree(d->cp_counts);
+    if (d->alt_p) cudaFree(d->alt_p);
+    if (d->alt_m) cudaFree(d->alt_m);
+    if (d->lod_gather) cudaFree(d->lod_gather);
+    if (d->ev) cudaEventDestroy(d->ev);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     return ION_OK;

@@ -1,0 +1,36 @@
+// domain_internal.cuh -- private layout of ion_domain_t and the error helpers shared by api.cu and comm.cu.
+#pragma once
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+#include "lattice.cuh"
+
+struct ion_domain {
+    IonParams params;
+    int device;
+    cudaStream_t stream;
+    void* buf[ION_FIELD_COUNT];
+    size_t bytes[ION_FIELD_COUNT];
+    ion::KArgs k;
+    void* lod_sources;    // scratch of update_e_b_dynamic
+    uint32_t* cp_counts;  // scratch of the precompute compaction
+    void* alt_p;          // spare transfer buffers: receive side of peer copies / NCCL (see ion_exchange_transfer)
+    void* alt_m;
+    float* lod_gather;    // world * n_lod_own * 4 floats, allocated on first ion_comm_exchange_lods
+    cudaEvent_t ev;       // reusable ordering event (timing disabled)
+    float ecrf;
+};
+
+namespace ion {
+extern std::atomic<uint64_t> g_launches;
+int fail(int code, const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void set_transfer_ptrs(ion_domain* d);  // refresh KArgs after the current/spare transfer buffers were flipped
+}  // namespace ion
+
+#define ION_CUDA(call)                                                  \
+    do {                                                                \
+        cudaError_t ion_e_ = (call);                                    \
+        if (ion_e_ != cudaSuccess) return ion::cuda_fail(ion_e_, #call); \
+    } while (0)

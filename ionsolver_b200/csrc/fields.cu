@@ -83,9 +83,11 @@ __global__ void k_build_sources(const __grid_constant__ KArgs a, LodSource* __re
             const uint32_t n_fd = to_d3(1u << depth);
             if (rem < n_fd) {
                 lod_coordinates(a, rem, depth, s.cx, s.cy, s.cz);
-                s.cx -= (float)(ddx * (int)a.nx);  // sim.cl:970-972 (halo-inclusive shift: quirk Q8)
-                s.cy -= (float)(ddy * (int)a.ny);
-                s.cz -= (float)(ddz * (int)a.nz);
+                // sim.cl:970-972: halo-inclusive shift (quirk Q8); `domain_diff.x * DEF_NX` is int * uint = uint in
+                // OpenCL C, so a negative domain difference wraps to ~4.29e9 before the float conversion (quirk Q18)
+                s.cx -= (float)((uint32_t)ddx * a.nx);
+                s.cy -= (float)((uint32_t)ddy * a.ny);
+                s.cz -= (float)((uint32_t)ddz * a.nz);
                 entry = offset + rem;
                 break;
             }

@@ -163,7 +163,11 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                 if (a.dx > 1u || a.dy > 1u || a.dz > 1u) {
                     for (uint32_t d = 0u; d < a.lod_depth; d++) off += 1u << (d * (uint32_t)VSet<VS>::DIM);
                 }
-                dep.ind = (lod_index(a, x, y, z, a.lod_depth) + off) * 4u;
+                // quirk Q7: on split axes the halo-inclusive division can point past the own finest level; entries
+                // inside the buffer are hit like in the reference, a deposit past DEF_NUM_LOD (undefined behaviour
+                // there) is dropped
+                const uint32_t li = lod_index(a, x, y, z, a.lod_depth) + off;
+                dep.ind = li < a.n_lod ? li * 4u : 0xFFFFFFFFu;
                 const float ils = 1.0f / lod_s(a, a.lod_depth);
                 dep.q = rhon_q - rhon_e;
                 dep.ux = uxn * ils;

@@ -364,10 +364,15 @@ static void stream_collide_cell(const Ctx* k, const OraBuffers* b, uint32_t n, u
                 for (uint32_t d = 0; d < p->lod_depth; d++) off += 1u << (d * k->dim);
             const uint32_t ind = (lod_index(k, n, p->lod_depth) + off) * 4;
             const float ils = 1.0f / lod_s(k, p->lod_depth);
+            /* quirk Q7: on split axes lod_index divides by the halo-inclusive size and can point past the own finest
+             * level; the reference then adds into foreign entries or, past DEF_NUM_LOD, outside the buffer (undefined
+             * behaviour).  The in-buffer case is reproduced, the out-of-buffer deposit is dropped. */
+            if (ind / 4 < p->n_lod) {
             atomic_add_f(&b->QU_lod[ind + 0], rhon_q - rhon_e);
             atomic_add_f(&b->QU_lod[ind + 1], uxn * ils);
             atomic_add_f(&b->QU_lod[ind + 2], uyn * ils);
             atomic_add_f(&b->QU_lod[ind + 3], uzn * ils);
+            }
         }
     }
 
@@ -577,9 +582,11 @@ void ora_update_e_b_dynamic(const OraParams* p, const OraBuffers* b) {
             for (uint32_t l = 0; l < n_lod_fd; l++) {
                 float lc[3];
                 lod_coordinates(&k, l, depth, lc);
-                lc[0] -= (float)(ddx * (int)p->nx);  /* quirk Q8 */
-                lc[1] -= (float)(ddy * (int)p->ny);
-                lc[2] -= (float)(ddz * (int)p->nz);
+                /* quirk Q8 (halo-inclusive shift) and Q18: `domain_diff.x * DEF_NX` is int * uint = uint in OpenCL C, so a
+                 * negative difference wraps to ~4.29e9 before the float conversion (sim.cl:970-972) */
+                lc[0] -= (float)((uint32_t)ddx * p->nx);
+                lc[1] -= (float)((uint32_t)ddy * p->ny);
+                lc[2] -= (float)((uint32_t)ddz * p->nz);
                 const float q_c = b->QU_lod[(offset + l) * 4 + 0];
                 const float v_c[3] = {b->QU_lod[(offset + l) * 4 + 1], b->QU_lod[(offset + l) * 4 + 2], b->QU_lod[(offset + l) * 4 + 3]};
                 const float r[3] = {cf[0] - lc[0], cf[1] - lc[1], cf[2] - lc[2]};

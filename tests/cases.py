@@ -1,0 +1,151 @@
+"""Shared test matrix: the configurations every parity test, the golden-vector generator and build() iterate over.
+
+A case is an `oracle.ref_host.RefConfig` (the oracle's statement of LbmConfig).  `to_lbm_config` turns it into the
+product's `ionsolver_b200.lbm.LbmConfig`; `fill_inputs` produces the seeded synthetic state both sides start from.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import ref_host as rh  # noqa: E402
+
+C = rh.RefConfig
+STL_DIR = os.path.join(ROOT, "tests", "golden", "stl")
+
+
+def _mhd(c, length=32.0, weak=False):
+    """setup_bfield_spin-style units (setup.rs:144); `weak` scales the charge unit so that the Coulomb coupling stays
+    small and the dynamics are well conditioned for multi-step comparisons."""
+    c.units.set(length, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 1e-7 if weak else 1e-10, 1.0)
+    return c
+
+
+def single_domain_cases():
+    """(name, RefConfig): every (velocity set x collision x storage x extension) family the reference can build,
+    on odd sizes that exercise the periodic wrap."""
+    return [
+        ("d3q19_fp32_srt", C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=24, n_z=20, nu=0.1, graphics_active=True)),
+        ("d3q19_fp32_trt_eqb_ff", C(velocity_set="D3Q19", float_type="FP32", relaxation_time="TRT", n_x=33, n_y=17, n_z=9, nu=0.02,
+                                    ext_equilibrium_boudaries=True, ext_volume_force=True, ext_force_field=True, f_x=1e-4, f_y=-2e-4,
+                                    f_z=3e-4, graphics_active=True)),
+        ("d3q19_fp16s_srt_vf", C(velocity_set="D3Q19", float_type="FP16S", n_x=32, n_y=16, n_z=16, nu=0.05, ext_volume_force=True,
+                                 f_x=1e-4, graphics_active=True)),
+        ("d3q19_fp16c_trt", C(velocity_set="D3Q19", float_type="FP16C", relaxation_time="TRT", n_x=32, n_y=16, n_z=16, nu=0.05,
+                              graphics_active=True)),
+        ("d3q27_fp32_srt_eqb", C(velocity_set="D3Q27", float_type="FP32", n_x=20, n_y=16, n_z=12, nu=0.05,
+                                 ext_equilibrium_boudaries=True, graphics_active=True)),
+        ("d3q15_fp16s_trt_vf", C(velocity_set="D3Q15", float_type="FP16S", relaxation_time="TRT", n_x=20, n_y=16, n_z=12, nu=0.05,
+                                 ext_volume_force=True, f_z=1e-4)),
+        ("d2q9_fp32_srt_vf", C(velocity_set="D2Q9", float_type="FP32", n_x=40, n_y=30, n_z=1, nu=0.05, ext_volume_force=True,
+                               f_x=1e-4, graphics_active=True)),
+        ("d3q27_fp16c_trt_vf_big", C(velocity_set="D3Q27", float_type="FP16C", relaxation_time="TRT", n_x=300, n_y=5, n_z=3, nu=0.03,
+                                     ext_volume_force=True, f_y=1e-4, graphics_active=True)),
+    ]
+
+
+def mhd_cases():
+    return [
+        ("mhd_d3q19_fp32_lod3", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=32, n_z=32, nu=0.05, ext_volume_force=True,
+                                      ext_magneto_hydro=True, mhd_lod_depth=3, graphics_active=True))),
+        ("mhd_d3q19_fp32_lod2", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=32, n_z=32, nu=0.05, ext_volume_force=True,
+                                      ext_magneto_hydro=True, mhd_lod_depth=2))),
+        ("mhd_d3q27_fp16c_lod1", _mhd(C(velocity_set="D3Q27", float_type="FP16C", n_x=16, n_y=16, n_z=16, nu=0.05, ext_volume_force=True,
+                                       ext_magneto_hydro=True, mhd_lod_depth=1, graphics_active=True), 16.0)),
+        ("mhd_d3q19_fp16s_lod2_eqb", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=24, n_y=16, n_z=20, nu=0.05, ext_volume_force=True,
+                                           ext_equilibrium_boudaries=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True), 24.0)),
+    ]
+
+
+def multi_domain_cases():
+    """Split lattices; the halo layout, flags in halos and (without MHD) every field have to stay bit-exact."""
+    return [
+        ("z2_d3q19_fp32", C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=12, n_z=20, d_z=2, nu=0.05, graphics_active=True)),
+        ("z3_d3q19_fp16s_trt", C(velocity_set="D3Q19", float_type="FP16S", relaxation_time="TRT", n_x=16, n_y=8, n_z=18, d_z=3, nu=0.05,
+                                 ext_volume_force=True, f_x=1e-4)),
+        ("x2y2_d3q27_fp32", C(velocity_set="D3Q27", float_type="FP32", n_x=12, n_y=16, n_z=6, d_x=2, d_y=2, nu=0.05, graphics_active=True)),
+        ("x2y2z2_d3q15_fp16c", C(velocity_set="D3Q15", float_type="FP16C", n_x=12, n_y=8, n_z=8, d_x=2, d_y=2, d_z=2, nu=0.05)),
+        ("x2_d2q9_fp32", C(velocity_set="D2Q9", float_type="FP32", n_x=24, n_y=18, n_z=1, d_x=2, nu=0.05, graphics_active=True)),
+    ]
+
+
+def multi_domain_mhd_cases():
+    """Halo-inclusive local sizes are multiples of 2^depth: otherwise the reference's LOD deposit writes outside
+    QU_lod (quirk Q7, undefined behaviour) and there is nothing to compare against."""
+    return [
+        ("mhd_z2_d3q19_fp32_lod2", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
+                                         ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True))),
+        ("mhd_z4_d3q19_fp16s_lod1", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=8, n_y=8, n_z=24, d_z=4, nu=0.05,
+                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=1), 8.0)),
+    ]
+
+
+def all_cases():
+    return single_domain_cases() + mhd_cases() + multi_domain_cases() + multi_domain_mhd_cases()
+
+
+def fill_inputs(lbm, cfg, seed=1, smooth=False):
+    """Seeded synthetic state written into an oracle RefLbm (numpy buffers).  Halo cells are filled too: the
+    initial communicate_rho_u_flags overwrites them, which is part of what is tested."""
+    rng = np.random.default_rng(seed)
+    amp = 0.01 if smooth else 0.05
+    for d in lbm.domains:
+        n = d.g.n
+        d.rho[:] = (1.0 + amp * rng.standard_normal(n)).astype(np.float32)
+        d.u[:] = (amp * rng.standard_normal(3 * n)).astype(np.float32)
+        fl = np.zeros(n, np.uint8)
+        r = rng.random(n)
+        fl[r < 0.05] = 0x01
+        if cfg.ext_equilibrium_boudaries:
+            fl[(r >= 0.05) & (r < 0.08)] = 0x02
+        fl[(r >= 0.08) & (r < 0.09)] = 0x11  # magnet-flagged cells are fluid to stream_collide (quirk Q1)
+        d.flags[:] = fl
+        if cfg.ext_force_field:
+            d.f[:] = (1e-4 * rng.standard_normal(3 * n)).astype(np.float32)
+        if cfg.ext_magneto_hydro:
+            d.qc[:] = (0.002 + 0.0005 * rng.standard_normal(n)).astype(np.float32)
+            d.b_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
+            d.e_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
+
+
+VS = {"D2Q9": 0, "D3Q15": 1, "D3Q19": 2, "D3Q27": 3}
+RT = {"SRT": 0, "TRT": 1}
+FT = {"FP16S": 0, "FP16C": 1, "FP32": 2}
+
+
+def to_lbm_config(cfg):
+    """RefConfig -> product LbmConfig (same field names as mod.rs:46-101)."""
+    from ionsolver_b200 import lbm as L
+    u = cfg.units
+    return L.LbmConfig(
+        velocity_set=VS[cfg.velocity_set], relaxation_time=RT[cfg.relaxation_time], float_type=FT[cfg.float_type],
+        units=L.Units(float(u.m), float(u.kg), float(u.s), float(u.a), float(u.k)),
+        n_x=cfg.n_x, n_y=cfg.n_y, n_z=cfg.n_z, d_x=cfg.d_x, d_y=cfg.d_y, d_z=cfg.d_z, nu=float(np.float32(cfg.nu)),
+        f_x=cfg.f_x, f_y=cfg.f_y, f_z=cfg.f_z, ext_equilibrium_boudaries=cfg.ext_equilibrium_boudaries,
+        ext_volume_force=cfg.ext_volume_force, ext_force_field=cfg.ext_force_field, ext_magneto_hydro=cfg.ext_magneto_hydro,
+        ext_subgrid_ecr=cfg.ext_subgrid_ecr, mhd_lod_depth=cfg.mhd_lod_depth, ecr_freq=cfg.ecr_freq,
+        graphics_config=L.GraphicsConfig(cfg.graphics_active))
+
+
+# oracle buffer name -> product field id (include/ionsolver_b200.h enum IonField)
+FIELD_OF = {"fi": 0, "rho": 1, "u": 2, "flags": 3, "f": 4, "e_stat": 5, "b_stat": 6, "e_dyn": 7, "b_dyn": 8, "fqi": 9, "ei": 10,
+            "qc": 11, "qu_lod": 12, "transfer_p": 16, "transfer_m": 17}
+
+
+def upload_inputs(ref_lbm, gpu_lbm):
+    """Copy the oracle's input state (rho, u, flags, F, Q, static fields) into the product's domains."""
+    cfg = ref_lbm.config
+    for rd, gd in zip(ref_lbm.domains, gpu_lbm.domains):
+        for name in ("rho", "u", "flags"):
+            gd.write(FIELD_OF[name], getattr(rd, name))
+        if cfg.ext_force_field:
+            gd.write(FIELD_OF["f"], rd.f)
+        if cfg.ext_magneto_hydro:
+            for name in ("qc", "b_stat", "e_stat"):
+                gd.write(FIELD_OF[name], getattr(rd, name))
