@@ -262,11 +262,14 @@ int ion_lbm_encode(ion_lbm_t* l, int reference_compatible, uint8_t** data, size_
 int ion_lbm_decode(const uint8_t* data, size_t len, IonLbmConfig* cfg, int reference_compatible, const int* devices, int n_devices, ion_lbm_t** out) {
     if (!data || !cfg || !out) return ion::fail(ION_ERR_INVALID, "NULL argument");
     *out = nullptr;
+    LbmConfig c = to_cpp(*cfg);
+    struct WriteBack {  // decode fills `config` in place as it parses (file.rs:54-104), also when it fails later
+        LbmConfig& c; IonLbmConfig* o; Lbm* lbm = nullptr;
+        ~WriteBack() { to_c(lbm ? lbm->config : c, o); }
+    } wb{c, cfg};
     ION_TRY({
-        LbmConfig c = to_cpp(*cfg);
-        Lbm* lbm = file::decode(std::vector<uint8_t>(data, data + len), c, reference_compatible != 0, devs(devices, n_devices));
-        to_c(lbm->config, cfg);
-        wrap_new(lbm, out);
+        wb.lbm = file::decode(std::vector<uint8_t>(data, data + len), c, reference_compatible != 0, devs(devices, n_devices));
+        wrap_new(wb.lbm, out);
     })
 }
 int ion_lbm_write_file(ion_lbm_t* l, const char* path) { ION_NEED(l); if (!path) return ion::fail(ION_ERR_INVALID, "NULL path"); ION_TRY(file::write(*l->lbm, path)) }

@@ -64,8 +64,8 @@ def main():
     write_stl(os.path.join(OUT, "disk_magnet.stl"), ring(0.05, 0.0, -0.005, 0.005, 64), "ionsolver_b200 synthetic disk magnet")
     write_stl(os.path.join(OUT, "ring_magnet.stl"), ring(0.05, 0.03, -0.005, 0.005, 32), "ionsolver_b200 synthetic ring magnet")
     write_stl(os.path.join(OUT, "tube.stl"), ring(0.025, 0.022, 0.03, 0.13, 32), "ionsolver_b200 synthetic quartz tube")
-    write_stl(os.path.join(OUT, "plate1.stl"), box((-0.015, 0.045, 0.0257), (0.015, 0.095, 0.0267)), "ionsolver_b200 synthetic e-plate 1")
-    write_stl(os.path.join(OUT, "plate2.stl"), box((-0.015, 0.045, -0.0267), (0.015, 0.095, -0.0257)), "ionsolver_b200 synthetic e-plate 2")
+    write_stl(os.path.join(OUT, "plate1.stl"), box((-0.015, 0.045, 0.024), (0.015, 0.095, 0.028)), "ionsolver_b200 synthetic e-plate 1")
+    write_stl(os.path.join(OUT, "plate2.stl"), box((-0.015, 0.045, -0.028), (0.015, 0.095, -0.024)), "ionsolver_b200 synthetic e-plate 2")
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -1,0 +1,154 @@
+"""Host layer without a GPU: Units, LbmConfig defaults, get_device_defines-equivalent parameters, JSON config I/O and
+.ion parsing errors, checked against the oracle's restatement of the Rust host (oracle/ref_host.py) and against the
+literal values in the reference sources."""
+import ctypes
+import json
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import cases
+from ionsolver_b200 import capi, lbm as L
+from oracle import ref_host as rh
+
+UNIT_SETS = [
+    (128.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0),     # setup.rs:144
+    (1.0, 1.0, 1.0, 1.0, 1.0, 0.5, 1.0, 1.0, 10.0, 1.0),                   # setup.rs:205
+    (1.0, 1.0, 1.0, 1.0, 1.0, 0.01, 10000.0, 10E-8, 0.0000000000001, 50000.0),  # setup.rs:282
+    (128.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 10e-8, 1.0, 50000.0),            # setup.rs:397
+]
+
+
+@pytest.mark.parametrize("args", UNIT_SETS)
+def test_units_match_oracle_bit_for_bit(args):
+    u = L.Units()
+    u.set(*args)
+    r = rh.Units()
+    r.set(*args)
+    for name in ("m", "kg", "s", "a", "k"):
+        assert np.float32(getattr(u, name)) == getattr(r, name), name
+    pairs = [("epsilon_0_lu", r.epsilon_0_lu()), ("ke_lu", r.ke_lu()), ("mu_0_lu", r.mu_0_lu()), ("kkge_lu", r.kkge_lu()),
+             ("kimg_lu", r.kimg_lu()), ("kveV_lu", r.kveV_lu()), ("kkBme_lu", r.kkBme_lu()), ("keabs_lu", r.keabs_lu()),
+             ("kme_lu", r.kme_lu())]
+    for name, want in pairs:
+        got = np.float32(getattr(u, name)())
+        assert got == want or (np.isnan(got) and np.isnan(want)) or (np.isinf(got) and np.isinf(want)), (name, got, want)
+    for name, v in (("len_si_lu", 0.37), ("nu_si_lu", 1.48e-5), ("charge_si_lu", 2.1e-13), ("mag_flux_si_lu", 0.0875),
+                    ("e_field_si_lu", 1000.0), ("magnetization_si_lu", 1.0e6), ("time_lu_si", 2.45e9)):
+        assert np.float32(getattr(u, name)(v)) == getattr(r, name)(v), name
+
+
+def test_lbm_config_defaults_are_the_reference_defaults():
+    c = L.LbmConfig()  # mod.rs:103-135
+    assert (c.velocity_set, c.relaxation_time, c.float_type) == (L.VelocitySet.D2Q9, L.RelaxationTime.Srt, L.FloatType.FP16S)
+    assert (c.n_x, c.n_y, c.n_z, c.d_x, c.d_y, c.d_z) == (1, 1, 1, 1, 1, 1)
+    assert np.float32(c.nu) == np.float32(1.0) / np.float32(6.0)
+    assert c.mhd_lod_depth == 4 and c.graphics_config.graphics_active is True
+    d = capi.IonLbmConfig()
+    capi.load().ion_lbm_config_default(d)
+    assert L.LbmConfig.from_c(d) == c
+
+
+ALL = cases.all_cases()
+
+
+@pytest.mark.parametrize("name,cfg", ALL, ids=[c[0] for c in ALL])
+def test_make_params_matches_get_device_defines(name, cfg):
+    """IonParams (the struct form of get_device_defines, domain.rs:736-858) against the oracle's #define block."""
+    pc = cases.to_lbm_config(cfg)
+    rcfg = rh.RefLbm.__new__(rh.RefLbm)  # only for the resolution rounding rule
+    n_d = cfg.d_x * cfg.d_y * cfg.d_z
+    for d in range(n_d):
+        x, y, z = rh.domain_coords(d, cfg.d_x, cfg.d_y)
+        g = rh.domain_geometry(cfg, x, y, z, d)
+        p = pc.make_params(d)
+        assert (p.nx, p.ny, p.nz) == (g.n_x, g.n_y, g.n_z)
+        assert (p.ox, p.oy, p.oz) == (g.o_x, g.o_y, g.o_z)
+        assert (p.dx, p.dy, p.dz, p.di) == (cfg.d_x, cfg.d_y, cfg.d_z, d)
+        assert (p.n_lod, p.n_lod_own, p.lod_depth) == (g.n_lod, g.n_lod_own, cfg.mhd_lod_depth)
+        defines = dict(re.findall(r"#define (\w+) (\S+)", rh.device_defines(cfg, g)))
+
+        def lit(key):
+            return np.float32(float(defines[key].rstrip("f")))
+        assert np.float32(p.w) == lit("DEF_W")
+        if cfg.ext_magneto_hydro:
+            for key, val in (("DEF_KE", p.ke), ("DEF_KMU", p.kmu), ("DEF_KMU0", p.kmu0), ("DEF_KKGE", p.kkge), ("DEF_KIMG", p.kimg),
+                             ("DEF_KVEV", p.kvev), ("DEF_KME", p.kme), ("DEF_WQ", p.wq)):
+                assert np.float32(val) == lit(key), key
+        ext = (1 * cfg.ext_equilibrium_boudaries | 2 * cfg.ext_volume_force | 4 * cfg.ext_force_field | 8 * cfg.ext_magneto_hydro
+               | 32 * cfg.graphics_active)
+        assert p.ext == ext
+
+
+def test_lod_counts_of_the_reference_scenes():
+    # setup_bfield_spin (setup.rs:142-156): 128x128x256, d_z = 2, depth 4 -> own 4681, + one foreign level 3 (512)
+    c = L.LbmConfig(velocity_set=L.VelocitySet.D3Q19, n_x=128, n_y=128, n_z=256, d_z=2, ext_volume_force=True, ext_magneto_hydro=True)
+    p = c.make_params(1)
+    assert (p.n_lod_own, p.n_lod) == (4681, 4681 + 512)
+    assert (p.nx, p.ny, p.nz, p.oz) == (128, 128, 130, 127)
+    # resolution is rounded down to a multiple of the domain count (mod.rs:167-179)
+    c = L.LbmConfig(velocity_set=L.VelocitySet.D3Q19, n_x=10, n_y=10, n_z=11, d_z=2)
+    assert c.make_params(0).nz == 5 + 2
+
+
+def test_velocity_set_tables():
+    assert [rh.SET_VALUES[k] for k in ("D2Q9", "D3Q15", "D3Q19", "D3Q27")] == [(2, 9, 3), (3, 15, 5), (3, 19, 5), (3, 27, 9)]
+    assert capi.SET_VALUES == {0: (2, 9, 3), 1: (3, 15, 5), 2: (3, 19, 5), 3: (3, 27, 9)}  # types.rs:37-46
+    assert (L.FloatType.size_of(L.FloatType.FP16S), L.FloatType.size_of(L.FloatType.FP16C), L.FloatType.size_of(L.FloatType.FP32)) == (2, 2, 4)
+
+
+def test_json_config_round_trip_and_serde_shape():
+    c = L.LbmConfig(velocity_set=L.VelocitySet.D3Q19, relaxation_time=L.RelaxationTime.Trt, float_type=L.FloatType.FP16C, n_x=128,
+                    n_y=256, n_z=128, d_z=2, nu=0.05, f_x=1e-5, ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=3,
+                    ecr_freq=0.5, run_steps=77, graphics_config=L.GraphicsConfig(False))
+    c.units.set(128.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
+    text = c.to_json()
+    j = json.loads(text)  # what serde_json::to_vec(&LbmConfig) produces: unit-variant enums as strings, nested structs as objects
+    assert j["velocity_set"] == "D3Q19" and j["relaxation_time"] == "Trt" and j["float_type"] == "FP16C"
+    assert j["units"]["prop"] == "H" and j["graphics_config"]["graphics_active"] is False
+    assert set(j) == {"velocity_set", "relaxation_time", "float_type", "units", "n_x", "n_y", "n_z", "d_x", "d_y", "d_z", "nu", "f_x", "f_y",
+                      "f_z", "ext_equilibrium_boudaries", "ext_volume_force", "ext_force_field", "ext_magneto_hydro", "ext_subgrid_ecr",
+                      "mhd_lod_depth", "ecr_freq", "ecr_field_strength", "graphics_config", "run_steps"}
+    assert "keyframes" in j["graphics_config"] and j["graphics_config"]["camera_width"] == 1920  # GraphicsConfig::new, graphics.rs:158-193
+    back = L.LbmConfig.from_json(text)
+    assert bytes(back.to_c()) == bytes(c.to_c())  # every f32 survives the text round trip bit for bit
+    # a config written by a real IonSolver build (extra graphics fields, any key order, whitespace) parses
+    j["graphics_config"]["v_max"] = 500.0
+    j["graphics_config"]["keyframes"] = [{"time": 3, "repeat": True, "cam_zoom": 1.5, "note": "a } brace in a string"}]
+    again = L.LbmConfig.from_json(json.dumps(dict(reversed(list(j.items()))), indent=2))
+    assert bytes(again.to_c()) == bytes(c.to_c())
+    with pytest.raises(capi.IonError):
+        L.LbmConfig.from_json('{"velocity_set":"D4Q99"}')
+    with pytest.raises(capi.IonError):
+        L.LbmConfig.from_json('{"n_x": }')
+
+
+def ion_header(ft=2, n=(4, 4, 4), d=(1, 1, 1), ext=0, vs=2):
+    b = b"IonSolver setup\n" + bytes([vs, 0, ft]) + struct.pack("<4f", 1, 1, 1, 1) + struct.pack("<3I", *n) + b"\0" + \
+        struct.pack("<3I", *d) + struct.pack("<4f", 1 / 6, 0, 0, 0) + bytes([ext, 4])
+    assert len(b) == 16 + 62  # FILE_LAYOUT.txt
+    return b
+
+
+def test_ion_decode_rejects_bad_files_before_touching_the_gpu():
+    lib = capi.load()
+    h = ctypes.c_void_p()
+    c = capi.IonLbmConfig()
+    lib.ion_lbm_config_default(c)
+    bad = b"NotIonSolver....\n" + b"\0" * 100
+    assert lib.ion_lbm_decode(bad, len(bad), c, 1, None, 0, ctypes.byref(h)) == capi.ION_ERR_INVALID
+    assert b"Invalid Format!" in lib.ion_last_error_string()  # file.rs:50-52
+    trunc = ion_header()[:40]
+    assert lib.ion_lbm_decode(trunc, len(trunc), c, 1, None, 0, ctypes.byref(h)) == capi.ION_ERR_RANGE
+    short = ion_header() + b"\0" * 10  # sections missing
+    assert lib.ion_lbm_decode(short, len(short), c, 1, None, 0, ctypes.byref(h)) == capi.ION_ERR_RANGE
+    assert not h.value
+    # the header fields land in the config before the payload check (decode fills `config` in place, file.rs:54-104)
+    hdr = ion_header(ft=1, n=(8, 6, 4), d=(1, 1, 2), ext=0b1010)
+    lib.ion_lbm_decode(hdr, len(hdr), c, 0, None, 0, ctypes.byref(h))
+    assert (c.n_x, c.n_y, c.n_z, c.d_z, c.ext_volume_force, c.ext_magneto_hydro, c.ext_force_field) == (8, 6, 4, 2, 1, 1, 0)
+    assert c.float_type == L.FloatType.FP16C      # FILE_LAYOUT / types.rs discriminant
+    lib.ion_lbm_decode(hdr, len(hdr), c, 1, None, 0, ctypes.byref(h))
+    assert c.float_type == L.FloatType.FP16S      # the reference decoder's swapped table, file.rs:68-73
