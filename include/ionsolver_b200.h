@@ -49,7 +49,13 @@ enum IonExt {
     ION_EXT_FORCE_FIELD = 1u << 2,
     ION_EXT_MAGNETO_HYDRO = 1u << 3,
     ION_EXT_SUBGRID_ECR = 1u << 4,
-    ION_EXT_UPDATE_FIELDS = 1u << 5 /* graphics_active => UPDATE_FIELDS, domain.rs:856 */
+    ION_EXT_UPDATE_FIELDS = 1u << 5, /* graphics_active => UPDATE_FIELDS, domain.rs:856 */
+    /* No reference equivalent.  The reference's LOD deposit uses float atomics (sim_kernels.cl:673-676), so its E/B
+     * fields depend on the execution order of the device and are not reproducible run to run.  With this bit the LOD
+     * sums are formed in ascending cell order and update_e_b_dynamic uses the reference's exact arithmetic (sqrt,
+     * cube, IEEE division, unfused sums) in the reference's loop order: every field is then bit-identical to the
+     * reference kernels executed sequentially.  Needs nx, ny, nz (halo-inclusive) divisible by 2^lod_depth. */
+    ION_EXT_DETERMINISTIC = 1u << 6
 };
 
 /* flag bits, src/lbm/domain.rs:819-828 (runtime values, not the IDE placeholders of sim_kernels.cl:45-54) */

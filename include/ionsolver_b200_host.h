@@ -32,7 +32,7 @@ typedef struct IonLbmConfig {
     uint8_t ext_equilibrium_boudaries, ext_volume_force, ext_force_field, ext_magneto_hydro, ext_subgrid_ecr;
     uint8_t mhd_lod_depth;
     uint8_t graphics_active;  /* graphics_config.graphics_active: the only graphics switch that reaches the kernels */
-    uint8_t reserved;
+    uint8_t deterministic;    /* B200 extension, not in the reference: ION_EXT_DETERMINISTIC (reproducible, reference-ordered E/B) */
     float ecr_freq, ecr_field_strength;
     uint64_t run_steps;
 } IonLbmConfig;

@@ -27,7 +27,7 @@ SET_VALUES = {D2Q9: (2, 9, 3), D3Q15: (3, 15, 5), D3Q19: (3, 19, 5), D3Q27: (3, 
 TRANSFER_FI, TRANSFER_RHO_U_FLAGS, TRANSFER_EI, TRANSFER_QI = 0, 1, 2, 3
 # enum IonExt
 EXT_EQUILIBRIUM_BOUNDARIES, EXT_VOLUME_FORCE, EXT_FORCE_FIELD = 1, 2, 4
-EXT_MAGNETO_HYDRO, EXT_SUBGRID_ECR, EXT_UPDATE_FIELDS = 8, 16, 32
+EXT_MAGNETO_HYDRO, EXT_SUBGRID_ECR, EXT_UPDATE_FIELDS, EXT_DETERMINISTIC = 8, 16, 32, 64
 # enum IonField
 (FIELD_FI, FIELD_RHO, FIELD_U, FIELD_FLAGS, FIELD_F, FIELD_E_STAT, FIELD_B_STAT, FIELD_E_DYN, FIELD_B_DYN, FIELD_FQI,
  FIELD_EI, FIELD_Q, FIELD_QU_LOD, FIELD_E_VAR, FIELD_ETI, FIELD_ET, FIELD_TRANSFER_P, FIELD_TRANSFER_M) = range(18)
@@ -94,7 +94,7 @@ class IonLbmConfig(ctypes.Structure):
         ("f_x", ctypes.c_float), ("f_y", ctypes.c_float), ("f_z", ctypes.c_float),
         ("ext_equilibrium_boudaries", ctypes.c_uint8), ("ext_volume_force", ctypes.c_uint8),
         ("ext_force_field", ctypes.c_uint8), ("ext_magneto_hydro", ctypes.c_uint8), ("ext_subgrid_ecr", ctypes.c_uint8),
-        ("mhd_lod_depth", ctypes.c_uint8), ("graphics_active", ctypes.c_uint8), ("reserved", ctypes.c_uint8),
+        ("mhd_lod_depth", ctypes.c_uint8), ("graphics_active", ctypes.c_uint8), ("deterministic", ctypes.c_uint8),
         ("ecr_freq", ctypes.c_float), ("ecr_field_strength", ctypes.c_float),
         ("run_steps", ctypes.c_uint64),
     ]

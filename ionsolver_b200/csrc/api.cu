@@ -18,9 +18,10 @@ cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt,
                                      cudaStream_t s);
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
-cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches);
+cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, bool exact);
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di);
 cudaError_t launch_clear_qu_lod(const KArgs& a, cudaStream_t s);
+cudaError_t launch_lod_deposit_ordered(const KArgs& a, cudaStream_t s);
 cudaError_t launch_lod_gather(const KArgs& a, cudaStream_t s, uint64_t* launches);
 cudaError_t launch_transfer(const KArgs& p, int vs, int fp, int transfer_field, int insert, uint32_t direction, uint64_t t,
                             cudaStream_t s);
@@ -112,6 +113,11 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
         if ((uint64_t)(p->nx + 2u) * (p->ny + 2u) * (p->nz + 2u) > 3ull * n) return fail(ION_ERR_UNSUPPORTED, "padded psi grid does not fit the E_dyn scratch (sim_kernels.cl:1234, domain.rs:280)");
     }
     if (ecr) return fail(ION_ERR_UNSUPPORTED, "SUBGRID_ECR is not built yet (SURVEY section 8 row f3)");
+    const bool deterministic = mhd && (p->ext & ION_EXT_DETERMINISTIC);
+    if (deterministic && p->lod_depth > 0u) {
+        const uint32_t nd = 1u << p->lod_depth;
+        if (p->nx % nd || p->ny % nd || p->nz % nd) return fail(ION_ERR_UNSUPPORTED, "ION_EXT_DETERMINISTIC needs nx, ny, nz (incl. halos) divisible by 2^lod_depth = %u", nd);
+    }
 
     int ndev = 0;
     cudaError_t ce = cudaGetDeviceCount(&ndev);
@@ -167,6 +173,10 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
     e = cudaEventCreateWithFlags(&d->ev, cudaEventDisableTiming);
     if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaEventCreate"); }
     if (mhd) {
+        if (deterministic) {
+            e = cudaMalloc((void**)&d->lod_u, n * 12);
+            if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc lod_u"); }
+        }
         e = cudaMalloc(&d->lod_sources, lod_source_bytes(p->lod_depth, p->n_lod_own, p->dx, p->dy, p->dz, p->di));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d->cp_counts, compaction_scratch_bytes(n));
         if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc scratch"); }
@@ -186,6 +196,8 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
     k.ei = d->buf[ION_FIELD_EI];
     k.Q = (float*)d->buf[ION_FIELD_Q];
     k.QU_lod = (float*)d->buf[ION_FIELD_QU_LOD];
+    k.lod_u = d->lod_u;
+    d->deterministic = deterministic;
     k.E_var = (const float*)d->buf[ION_FIELD_E_VAR];
     k.eti = d->buf[ION_FIELD_ETI];
     k.Et = (float*)d->buf[ION_FIELD_ET];
@@ -215,6 +227,7 @@ int ion_domain_destroy(ion_domain_t* d) {
         if (d->buf[f]) cudaFree(d->buf[f]);
     if (d->lod_sources) cudaFree(d->lod_sources);
     if (d->cp_counts) cudaFree(d->cp_counts);
+    if (d->lod_u) cudaFree(d->lod_u);
     if (d->alt_p) cudaFree(d->alt_p);
     if (d->alt_m) cudaFree(d->alt_m);
     if (d->lod_gather) cudaFree(d->lod_gather);
@@ -327,6 +340,11 @@ int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, 
     ION_VS_DISPATCH(launch_stream_collide_vs, d->k, (int)d->params.float_type, mhd, trt, t, fx, fy, fz, d->stream)
     g_launches++;
     if (e != cudaSuccess) return cuda_fail(e, "stream_collide launch");
+    if (mhd && d->deterministic && d->params.lod_depth > 0u) {  // ordered LOD sums instead of the in-kernel float atomics
+        e = launch_lod_deposit_ordered(d->k, d->stream);
+        g_launches++;
+        if (e != cudaSuccess) return cuda_fail(e, "lod_deposit_ordered launch");
+    }
     return ION_OK;
 }
 
@@ -352,7 +370,7 @@ int ion_enqueue_update_e_b_dyn(ion_domain_t* d) {
     if (r) return r;
     ION_CUDA(cudaSetDevice(d->device));
     uint64_t l = 0;
-    cudaError_t e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l);
+    cudaError_t e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l, d->deterministic);
     g_launches += l;
     if (e != cudaSuccess) return cuda_fail(e, "update_e_b_dynamic launch");
     return ION_OK;

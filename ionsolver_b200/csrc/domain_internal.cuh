@@ -17,9 +17,11 @@ struct ion_domain {
     uint32_t* cp_counts;  // scratch of the precompute compaction
     void* alt_p;          // spare transfer buffers: receive side of peer copies / NCCL (see ion_exchange_transfer)
     void* alt_m;
+    float* lod_u;         // deterministic mode: per-cell velocity deposits (3N floats)
     float* lod_gather;    // world * n_lod_own * 4 floats, allocated on first ion_comm_exchange_lods
     cudaEvent_t ev;       // reusable ordering event (timing disabled)
     float ecrf;
+    bool deterministic;   // ION_EXT_DETERMINISTIC: reference-ordered LOD sums and reference arithmetic in update_e_b_dynamic
 };
 
 namespace ion {

@@ -104,9 +104,41 @@ __global__ void k_build_sources(const __grid_constant__ KArgs a, LodSource* __re
     src[k] = s;
 }
 
+template <bool EXACT>
+__device__ __forceinline__ void pre_field(float rx, float ry, float rz, float& px, float& py, float& pz) {
+    if (EXACT) {  // vec_r / cbmagnitude(vec_r), sim.cl:91-94,931-932
+        const float l = sqrtf(rx * rx + ry * ry + rz * rz);
+        const float l3 = l * l * l;
+        px = rx / l3; py = ry / l3; pz = rz / l3;
+    } else {
+        const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
+        const float ri = r2 > 0.0f ? rsqrtf(r2) : 0.0f;
+        const float ri3 = ri * ri * ri;
+        px = rx * ri3; py = ry * ri3; pz = rz * ri3;
+    }
+}
+// e += q*pre; b += q*cross(v,pre)   (sim.cl:934-935).  Fast mode gets w = q*v from the staged table.
+template <bool EXACT>
+__device__ __forceinline__ void accumulate_pair(float* e, float* b, const float4 s, float px, float py, float pz, bool skip) {
+    if (EXACT) {
+        float tx = s.x * px, ty = s.x * py, tz = s.x * pz;
+        float cx = s.x * (s.z * pz - s.w * py), cy = s.x * (s.w * px - s.y * pz), cz = s.x * (s.y * py - s.z * px);
+        if (skip) { tx = ty = tz = cx = cy = cz = 0.0f; }
+        e[0] += tx; e[1] += ty; e[2] += tz;
+        b[0] += cx; b[1] += cy; b[2] += cz;
+    } else {
+        const float q = skip ? 0.0f : s.x, wx = skip ? 0.0f : s.y, wy = skip ? 0.0f : s.z, wz = skip ? 0.0f : s.w;
+        e[0] = fmaf(q, px, e[0]); e[1] = fmaf(q, py, e[1]); e[2] = fmaf(q, pz, e[2]);
+        b[0] = fmaf(wy, pz, fmaf(-wz, py, b[0]));
+        b[1] = fmaf(wz, px, fmaf(-wx, pz, b[1]));
+        b[2] = fmaf(wx, py, fmaf(-wy, px, b[2]));
+    }
+}
+
 constexpr int EB_BLOCK = 256;
 constexpr int EB_CHUNK = 1024;  // sources per shared-memory stage (32 KB)
 
+template <bool EXACT>
 __global__ void __launch_bounds__(EB_BLOCK) k_update_e_b(const __grid_constant__ KArgs a, const LodSource* __restrict__ src,
                                                           const uint32_t count) {
     __shared__ float4 s_pos[EB_CHUNK];  // cx,cy,cz,q
@@ -117,7 +149,7 @@ __global__ void __launch_bounds__(EB_BLOCK) k_update_e_b(const __grid_constant__
     if (active) active = (a.flags[n] & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:900-902
     const uint64_t N = a.N;
     const float px = (float)x, py = (float)y, pz = (float)z;
-    float ex = 0.f, ey = 0.f, ez = 0.f, bx = 0.f, by = 0.f, bz = 0.f;
+    float e[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
 
     // ---- close distance: individual cells of the near block (sim.cl:907-938) ----
     if (active) {
@@ -137,15 +169,11 @@ __global__ void __launch_bounds__(EB_BLOCK) k_update_e_b(const __grid_constant__
                         if (nc == n) continue;
                         const float qc = a.Q[nc];
                         if (qc == 0.0f) continue;
-                        const float vx = a.u[nc], vy = a.u[N + nc], vz = a.u[2ull * N + nc];
-                        const float rx = px - (float)xc, ry = py - (float)yc, rz = pz - (float)zc;
-                        const float ri = rsqrtf(fmaf(rx, rx, fmaf(ry, ry, rz * rz)));
-                        const float s = qc * (ri * ri * ri);
-                        const float gx = rx * s, gy = ry * s, gz = rz * s;
-                        ex += gx; ey += gy; ez += gz;
-                        bx += vy * gz - vz * gy;
-                        by += vz * gx - vx * gz;
-                        bz += vx * gy - vy * gx;
+                        float4 s = make_float4(qc, a.u[nc], a.u[N + nc], a.u[2ull * N + nc]);
+                        if (!EXACT) { s.y *= s.x; s.z *= s.x; s.w *= s.x; }
+                        float fx, fy, fz;
+                        pre_field<EXACT>(px - (float)xc, py - (float)yc, pz - (float)zc, fx, fy, fz);
+                        accumulate_pair<EXACT>(e, b, s, fx, fy, fz, false);
                     }
                 }
             }
@@ -160,7 +188,9 @@ __global__ void __launch_bounds__(EB_BLOCK) k_update_e_b(const __grid_constant__
         for (uint32_t k = threadIdx.x; k < m; k += blockDim.x) {
             const float4* p = reinterpret_cast<const float4*>(src + base + k);
             s_pos[k] = __ldg(p);
-            s_vel[k] = __ldg(p + 1);
+            float4 v = __ldg(p + 1);
+            if (!EXACT) { const float q = s_pos[k].w; v.x *= q; v.y *= q; v.z *= q; }
+            s_vel[k] = v;
         }
         __syncthreads();
         if (active) {
@@ -168,27 +198,212 @@ __global__ void __launch_bounds__(EB_BLOCK) k_update_e_b(const __grid_constant__
             for (uint32_t k = 0; k < m; k++) {
                 const float4 c = s_pos[k];
                 const float4 v = s_vel[k];
-                const float rx = px - c.x, ry = py - c.y, rz = pz - c.z;
-                const float r2 = fmaf(rx, rx, fmaf(ry, ry, rz * rz));
-                const float ri = rsqrtf(r2);
+                float fx, fy, fz;
+                pre_field<EXACT>(px - c.x, py - c.y, pz - c.z, fx, fy, fz);
                 // self-skip (sim.cl:944): the own LOD block contributes nothing (its centre may coincide with the cell)
-                const float s = (__float_as_uint(v.w) == ndi) ? 0.0f : c.w * (ri * ri * ri);
-                const float gx = rx * s, gy = ry * s, gz = rz * s;
-                ex += gx; ey += gy; ez += gz;
-                bx = fmaf(v.y, gz, fmaf(-v.z, gy, bx));
-                by = fmaf(v.z, gx, fmaf(-v.x, gz, by));
-                bz = fmaf(v.x, gy, fmaf(-v.y, gx, bz));
+                accumulate_pair<EXACT>(e, b, make_float4(c.w, v.x, v.y, v.z), fx, fy, fz, __float_as_uint(v.w) == ndi);
             }
         }
     }
     if (!active) return;
     // sim.cl:986-992
-    a.E_dyn[n] = a.E_stat[n] + a.ke * ex;
-    a.E_dyn[N + n] = a.E_stat[N + n] + a.ke * ey;
-    a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n] + a.ke * ez;
-    a.B_dyn[n] = a.B_stat[n] + a.kmu * bx;
-    a.B_dyn[N + n] = a.B_stat[N + n] + a.kmu * by;
-    a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n] + a.kmu * bz;
+    a.E_dyn[n] = a.E_stat[n] + a.ke * e[0];
+    a.E_dyn[N + n] = a.E_stat[N + n] + a.ke * e[1];
+    a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n] + a.ke * e[2];
+    a.B_dyn[n] = a.B_stat[n] + a.kmu * b[0];
+    a.B_dyn[N + n] = a.B_stat[N + n] + a.kmu * b[1];
+    a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n] + a.kmu * b[2];
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Tiled update_e_b_dynamic: the LOD source grid is regular, so r = cell - centre depends only on the block
+// DIFFERENCE along x and on the cell's offset inside its block.  A thread owns the ND cells of one x-row that share
+// the in-block offset ox (x = k*dsx + ox, k = 0..ND-1).  For one row of ND sources (fixed cy, cz) the ND x ND
+// (cell, source) pairs need only 2*ND-1 distinct r/|r|^3 vectors (a Toeplitz tile): those are evaluated once per
+// diagonal and reused by up to ND pairs, which cuts the work per pair from ~24 instructions (sub, 3 fma, rsqrt,
+// 6 mul, 3 add, 6 fma, 2 LDS) to the 9 FMAs of the accumulation plus 1/8 of a vector evaluation.
+//   EXACT = false: rsqrt-based r/|r|^3, fused accumulation, sources staged as (q, q*v).
+//   EXACT = true : the reference's arithmetic to the bit -- sqrt, cube, three IEEE divisions, unfused
+//                  `e += q*pre; b += q*cross(v,pre)` -- and, per cell, the reference's summation order (near cells,
+//                  own LODs by ascending index, foreign LODs); with the ordered LOD deposit this makes E_dyn/B_dyn
+//                  bit-identical to the reference kernels run sequentially.
+// Requirements: depth 3 or 4 (ND = 8 / 16) and nx % ND == 0; everything else (other depths, ragged x) uses
+// k_update_e_b above.  Quirks Q4/Q5/Q7/Q8/Q18 are reproduced: sources are addressed by their table index d, the
+// skipped own block is the one whose INDEX equals lod_index(cell), foreign levels keep their shifted centres.
+// ------------------------------------------------------------------------------------------------------
+constexpr int EBT_BLOCK = 128;
+static inline size_t fine_bytes(int nd) { return (size_t)nd * nd * nd * sizeof(float4); }
+
+template <int ND, bool EXACT>
+__global__ void __launch_bounds__(EBT_BLOCK) k_update_e_b_tiled(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
+                                                                  const uint32_t n_foreign) {
+    extern __shared__ float4 s_tab[];  // source table by index d - lo: (q, vx, vy, vz) or (q, q*vx, q*vy, q*vz)
+    const uint32_t fine = (uint32_t)ND * ND * ND;
+    const uint32_t lo = a.n_lod_own >= fine ? a.n_lod_own - fine : 0u;  // sim.cl:943
+    const uint32_t cnt = a.n_lod_own - lo;
+    for (uint32_t k = threadIdx.x; k < cnt; k += EBT_BLOCK) {
+        float4 v = __ldg(reinterpret_cast<const float4*>(a.QU_lod) + lo + k);
+        if (!EXACT) { v.y *= v.x; v.z *= v.x; v.w *= v.x; }
+        s_tab[k] = v;
+    }
+    __syncthreads();
+    const uint32_t dsx = a.nx / ND, dsy = a.ny / ND, dsz = a.nz / ND;
+    const uint32_t m = blockIdx.x * EBT_BLOCK + threadIdx.x;  // (ox, y) of this thread, z = blockIdx.y
+    if (m >= dsx * a.ny) return;
+    const uint32_t ox = m % dsx, y = m / dsx, z = blockIdx.y;
+    const uint64_t N = a.N;
+    const uint32_t row0 = y * a.nx + z * a.nx * a.ny;
+    const float fy = (float)y, fz = (float)z;
+    const float dsxf = (float)dsx, dsyf = (float)dsy, dszf = (float)dsz;
+    const uint32_t self_row = y / dsy + (z / dsz) * ND;  // (ndi - bx) / ND: row index of the skipped own block
+
+    float e[ND][3], b[ND][3];
+#pragma unroll
+    for (int k = 0; k < ND; k++) { e[k][0] = e[k][1] = e[k][2] = 0.0f; b[k][0] = b[k][1] = b[k][2] = 0.0f; }
+
+    // ---- close distance (sim.cl:907-938): only non-empty when nx >= 2^(2^depth+1), i.e. depth 3 and nx >= 512 ----
+    {
+        const uint32_t sh = 1u << ND;  // ND = 8 -> 256; ND = 16 -> 65536
+        const uint32_t nsx = a.nx / sh > 1u ? a.nx / sh : 1u, nsy = a.ny / sh > 1u ? a.ny / sh : 1u, nsz = a.nz / sh > 1u ? a.nz / sh : 1u;
+        if (nsx * nsy * nsz > 1u) {
+            for (int k = 0; k < ND; k++) {
+                const uint32_t x = (uint32_t)k * dsx + ox, n = row0 + x;
+                const uint32_t xu = min((x / nsx) * nsx + nsx, a.dx > 1u ? a.nx - 1u : a.nx);
+                const uint32_t yu = min((y / nsy) * nsy + nsy, a.dy > 1u ? a.ny - 1u : a.ny);
+                const uint32_t zu = min((z / nsz) * nsz + nsz, a.dz > 1u ? a.nz - 1u : a.nz);
+                float ek[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
+                for (uint32_t xc = max((x / nsx) * nsx, a.dx > 1u ? 1u : 0u); xc < xu; xc++)
+                    for (uint32_t yc = max((y / nsy) * nsy, a.dy > 1u ? 1u : 0u); yc < yu; yc++)
+                        for (uint32_t zc = max((z / nsz) * nsz, a.dz > 1u ? 1u : 0u); zc < zu; zc++) {
+                            const uint32_t nc = xc + (yc + zc * a.ny) * a.nx;
+                            if (nc == n) continue;
+                            const float qc = a.Q[nc];
+                            if (qc == 0.0f) continue;
+                            float4 s = make_float4(qc, a.u[nc], a.u[N + nc], a.u[2ull * N + nc]);
+                            if (!EXACT) { s.y *= s.x; s.z *= s.x; s.w *= s.x; }
+                            float px, py, pz;
+                            pre_field<EXACT>((float)x - (float)xc, fy - (float)yc, fz - (float)zc, px, py, pz);
+                            accumulate_pair<EXACT>(ek, bk, s, px, py, pz, false);
+                        }
+#pragma unroll
+                for (int kk = 0; kk < ND; kk++)
+                    if (kk == k) { e[kk][0] = ek[0]; e[kk][1] = ek[1]; e[kk][2] = ek[2]; b[kk][0] = bk[0]; b[kk][1] = bk[1]; b[kk][2] = bk[2]; }
+            }
+        }
+    }
+
+    // ---- own LODs, ascending index d = cx + ND*row (sim.cl:940-955) ----
+    const float rx0 = (float)ox - 0.5f * dsxf;  // r_x for block difference 0: (k*dsx+ox) - (cx*dsx + dsx/2), k == cx
+    const uint32_t row_lo = lo / ND, row_hi = (a.n_lod_own + ND - 1) / ND;
+    for (uint32_t row = row_lo; row < row_hi; row++) {
+        const uint32_t cy = row % ND, cz = row / ND;
+        const float ry = fy - ((float)cy * dsyf + 0.5f * dsyf);
+        const float rz = fz - ((float)cz * dszf + 0.5f * dszf);
+        const bool is_self = row == self_row;
+        const int d0 = (int)(row * ND) - (int)lo;  // table slot of cx = 0 (negative / past the end on the two ragged rows)
+        if (d0 < 0 || d0 + ND > (int)cnt) {
+            // ragged first / last row: entries outside [lo, n_lod_own) are not visited by the reference loop, so they
+            // cannot simply get a zero weight (0 * r/|r|^3 is NaN when the cell sits on that block's centre)
+            for (int k = 0; k < ND; k++) {
+                float ek[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
+                bool first = true;
+#pragma unroll
+                for (int kk = 0; kk < ND; kk++)
+                    if (kk == k) { ek[0] = e[kk][0]; ek[1] = e[kk][1]; ek[2] = e[kk][2]; bk[0] = b[kk][0]; bk[1] = b[kk][1]; bk[2] = b[kk][2]; }
+                for (int cx = 0; cx < ND; cx++) {
+                    const int slot = d0 + cx;
+                    if (slot < 0 || slot >= (int)cnt || (is_self && cx == k)) continue;
+                    float px, py, pz;
+                    pre_field<EXACT>((float)(k - cx) * dsxf + rx0, ry, rz, px, py, pz);
+                    accumulate_pair<EXACT>(ek, bk, s_tab[slot], px, py, pz, false);
+                }
+                (void)first;
+#pragma unroll
+                for (int kk = 0; kk < ND; kk++)
+                    if (kk == k) { e[kk][0] = ek[0]; e[kk][1] = ek[1]; e[kk][2] = ek[2]; b[kk][0] = bk[0]; b[kk][1] = bk[1]; b[kk][2] = bk[2]; }
+            }
+            continue;
+        }
+        // diagonals from +(ND-1) down to -(ND-1): for a fixed cell k the sources cx = k - D are then visited in
+        // ascending order, as in the reference loop
+#pragma unroll
+        for (int D = ND - 1; D >= -(ND - 1); D--) {
+            // r_x = (k - cx)*dsx + ox - dsx/2, evaluated like the reference: (float)x - ((float)cx*dsx + 0.5*dsx);
+            // every operand is a small integer or half-integer, so the value is exact and depends on D only
+            const float rx = (float)D * dsxf + rx0;
+            float px, py, pz;
+            pre_field<EXACT>(rx, ry, rz, px, py, pz);
+#pragma unroll
+            for (int k = 0; k < ND; k++) {
+                const int cx = k - D;
+                if (cx < 0 || cx >= ND) continue;
+                accumulate_pair<EXACT>(e[k], b[k], s_tab[d0 + cx], px, py, pz, (D == 0) && is_self);
+            }
+        }
+    }
+
+    // ---- foreign-domain LODs (sim.cl:957-983), flat list prepared by k_build_sources ----
+    for (uint32_t f = 0; f < n_foreign; f++) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(foreign + f));
+        float4 s = __ldg(reinterpret_cast<const float4*>(foreign + f) + 1);
+        s = make_float4(c.w, s.x, s.y, s.z);
+        if (!EXACT) { s.y *= s.x; s.z *= s.x; s.w *= s.x; }
+        const float ry = fy - c.y, rz = fz - c.z;
+#pragma unroll
+        for (int k = 0; k < ND; k++) {
+            float px, py, pz;
+            pre_field<EXACT>((float)((uint32_t)k * dsx + ox) - c.x, ry, rz, px, py, pz);
+            accumulate_pair<EXACT>(e[k], b[k], s, px, py, pz, false);
+        }
+    }
+
+    // ---- sim.cl:986-992 ----
+#pragma unroll
+    for (int k = 0; k < ND; k++) {
+        const uint32_t x = (uint32_t)k * dsx + ox;
+        const uint32_t n = row0 + x;
+        if (is_halo(a, x, y, z)) continue;
+        if ((a.flags[n] & ION_TYPE_BO) == ION_TYPE_S) continue;
+        a.E_dyn[n] = a.E_stat[n] + a.ke * e[k][0];
+        a.E_dyn[N + n] = a.E_stat[N + n] + a.ke * e[k][1];
+        a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n] + a.ke * e[k][2];
+        a.B_dyn[n] = a.B_stat[n] + a.kmu * b[k][0];
+        a.B_dyn[N + n] = a.B_stat[N + n] + a.kmu * b[k][1];
+        a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n] + a.kmu * b[k][2];
+    }
+}
+
+// Deterministic LOD deposit (ION_EXT_DETERMINISTIC): the reference adds every cell's (Q, u/cells) to its finest-level LOD
+// entry with float atomics (sim.cl:666-677), i.e. in execution order.  Here one thread per (entry, component) walks the
+// cells of its block in ascending cell index -- the order of a sequential run of the reference kernel -- so the sums
+// are reproducible and bit-identical to that run.  Needs block-aligned lattices (no lod_index overflow, quirk Q7).
+__global__ void k_lod_deposit_ordered(const __grid_constant__ KArgs a) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t nd = 1u << a.lod_depth;
+    const uint32_t entry = tid >> 2, comp = tid & 3u;
+    if (entry >= nd * nd * nd) return;
+    const uint32_t dsx = a.nx / nd, dsy = a.ny / nd, dsz = a.nz / nd;
+    const uint32_t bx = entry % nd, by = (entry / nd) % nd, bz = entry / (nd * nd);
+    uint32_t off = 0u;
+    if (a.dx > 1u || a.dy > 1u || a.dz > 1u)
+        for (uint32_t d = 0u; d < a.lod_depth; d++) off += 1u << (d * 3u);
+    const float* __restrict__ v = comp == 0u ? a.Q : a.lod_u + (uint64_t)(comp - 1u) * a.N;
+    float acc = a.QU_lod[(uint64_t)(entry + off) * 4u + comp];
+    for (uint32_t z = bz * dsz; z < (bz + 1u) * dsz; z++)
+        for (uint32_t y = by * dsy; y < (by + 1u) * dsy; y++)
+            for (uint32_t x = bx * dsx; x < (bx + 1u) * dsx; x++) {
+                if (is_halo(a, x, y, z)) continue;
+                const uint32_t n = x + (y + z * a.ny) * a.nx;
+                if ((a.flags[n] & ION_TYPE_BO) == ION_TYPE_S) continue;
+                acc += v[n];
+            }
+    a.QU_lod[(uint64_t)(entry + off) * 4u + comp] = acc;
+}
+cudaError_t launch_lod_deposit_ordered(const KArgs& a, cudaStream_t s) {
+    const uint32_t nd = 1u << a.lod_depth;
+    const uint32_t threads = nd * nd * nd * 4u;
+    k_lod_deposit_ordered<<<(threads + 63u) / 64u, 64, 0, s>>>(a);
+    return cudaGetLastError();
 }
 
 // clear_qu_lod, sim.cl:995-1003: global size n_lod (domain.rs:277), guard n > NUM_LOD_OWN (quirk Q12)
@@ -222,15 +437,37 @@ __global__ void k_lod_gather(float* __restrict__ lods, uint32_t depth) {
 }
 
 // ---- launchers used by api.cu ----
-cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches) {
+template <int ND, bool EXACT>
+static cudaError_t launch_tiled(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s) {
+    const size_t smem = (size_t)own * sizeof(float4);
+    if (smem > 48u * 1024u) {  // per device, so set on every launch (a host-side table lookup)
+        cudaError_t e = cudaFuncSetAttribute(k_update_e_b_tiled<ND, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fine_bytes(ND));
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t dsx = a.nx / ND;
+    const dim3 grid((dsx * a.ny + EBT_BLOCK - 1) / EBT_BLOCK, a.nz);
+    k_update_e_b_tiled<ND, EXACT><<<grid, EBT_BLOCK, smem, s>>>(a, src + own, count - own);
+    return cudaGetLastError();
+}
+
+// exact: reproduce the reference's arithmetic and summation order bit for bit (slower); see k_update_e_b_tiled
+cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, bool exact) {
     const uint32_t count = source_count(a.lod_depth, a.n_lod_own, a.dx, a.dy, a.dz, a.di);
     LodSource* src = reinterpret_cast<LodSource*>(scratch_sources);
     k_build_sources<<<(count + 255u) / 256u, 256, 0, s>>>(a, src, count);
+    *launches += 2;
+    const uint32_t nd = 1u << a.lod_depth;
+    const uint32_t fine = nd * nd * nd;
+    const uint32_t own = a.n_lod_own >= fine ? fine : a.n_lod_own;
+    if ((a.lod_depth == 3u || a.lod_depth == 4u) && a.nx % nd == 0u && a.n_lod_own >= fine && a.ny >= nd && a.nz >= nd) {
+        if (a.lod_depth == 4u) return exact ? launch_tiled<16, true>(a, src, own, count, s) : launch_tiled<16, false>(a, src, own, count, s);
+        return exact ? launch_tiled<8, true>(a, src, own, count, s) : launch_tiled<8, false>(a, src, own, count, s);
+    }
     unsigned b = ((a.nx + 31u) / 32u) * 32u;
     if (b > (unsigned)EB_BLOCK) b = EB_BLOCK;
     const dim3 grid((a.nx + b - 1u) / b, a.ny, a.nz);
-    k_update_e_b<<<grid, b, 0, s>>>(a, src, count);
-    *launches += 2;
+    if (exact) k_update_e_b<true><<<grid, b, 0, s>>>(a, src, count);
+    else k_update_e_b<false><<<grid, b, 0, s>>>(a, src, count);
     return cudaGetLastError();
 }
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di) {

@@ -31,6 +31,7 @@ LbmConfig to_cpp(const IonLbmConfig& c) {
     o.ext_magneto_hydro = c.ext_magneto_hydro; o.ext_subgrid_ecr = c.ext_subgrid_ecr;
     o.mhd_lod_depth = c.mhd_lod_depth;
     o.graphics_config.graphics_active = c.graphics_active;
+    o.deterministic = c.deterministic != 0;
     o.ecr_freq = c.ecr_freq; o.ecr_field_strength = c.ecr_field_strength;
     o.run_steps = c.run_steps;
     return o;
@@ -48,6 +49,7 @@ void to_c(const LbmConfig& c, IonLbmConfig* o) {
     o->ext_magneto_hydro = c.ext_magneto_hydro; o->ext_subgrid_ecr = c.ext_subgrid_ecr;
     o->mhd_lod_depth = c.mhd_lod_depth;
     o->graphics_active = c.graphics_config.graphics_active;
+    o->deterministic = c.deterministic;
     o->ecr_freq = c.ecr_freq; o->ecr_field_strength = c.ecr_field_strength;
     o->run_steps = c.run_steps;
 }

@@ -124,7 +124,8 @@ IonParams LbmDomain::make_params(const LbmConfig& c, uint32_t x, uint32_t y, uin
     p.float_type = (uint32_t)c.float_type;
     p.ext = (c.ext_equilibrium_boudaries ? ION_EXT_EQUILIBRIUM_BOUNDARIES : 0u) | (c.ext_volume_force ? ION_EXT_VOLUME_FORCE : 0u) |
             (c.ext_force_field ? ION_EXT_FORCE_FIELD : 0u) | (c.ext_magneto_hydro ? ION_EXT_MAGNETO_HYDRO : 0u) |
-            (c.ext_subgrid_ecr ? ION_EXT_SUBGRID_ECR : 0u) | (c.graphics_config.graphics_active ? ION_EXT_UPDATE_FIELDS : 0u);
+            (c.ext_subgrid_ecr ? ION_EXT_SUBGRID_ECR : 0u) | (c.graphics_config.graphics_active ? ION_EXT_UPDATE_FIELDS : 0u) |
+            (c.deterministic && c.ext_magneto_hydro ? ION_EXT_DETERMINISTIC : 0u);
     p.w = 1.0f / (3.0f * c.nu + 0.5f);  // domain.rs:808
     const Units& u = c.units;            // domain.rs:838-853
     p.ke = u.ke_lu();

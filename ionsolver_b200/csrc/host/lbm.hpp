@@ -97,6 +97,8 @@ struct LbmConfig {
     float ecr_field_strength = 0.0f;
     GraphicsConfig graphics_config;
     uint64_t run_steps = 0;
+    // not in the reference: reproducible, reference-ordered E/B path (ION_EXT_DETERMINISTIC in ionsolver_b200.h)
+    bool deterministic = false;
 };
 
 // ---- mesh.rs ---------------------------------------------------------------------------------------------------

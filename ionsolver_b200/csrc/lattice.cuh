@@ -30,6 +30,7 @@ struct KArgs {
     void* ei;
     float* Q;
     float* QU_lod;
+    float* lod_u;  // deterministic mode: per-cell scaled velocity deposit (3N floats), summed in order by k_lod_deposit_ordered
     const float* E_var;
     void* eti;
     float* Et;

@@ -240,7 +240,17 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
         ep_store<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 1, sim.cl:757
     }
 
-    if (MHD) lod_deposit_warp(a.QU_lod, dep);
+    if (MHD) {
+        if (a.ext & ION_EXT_DETERMINISTIC) {  // warp-uniform; the charge deposit is Q[n], already stored
+            if (dep.ind != 0xFFFFFFFFu) {
+                a.lod_u[n] = dep.ux;
+                a.lod_u[a.N + n] = dep.uy;
+                a.lod_u[2ull * a.N + n] = dep.uz;
+            }
+        } else {
+            lod_deposit_warp(a.QU_lod, dep);
+        }
+    }
 }
 
 // update_fields, sim.cl:834-859

@@ -111,6 +111,7 @@ class LbmConfig:
     ecr_field_strength: float = 0.0
     graphics_config: GraphicsConfig = dataclasses.field(default_factory=GraphicsConfig)
     run_steps: int = 0
+    deterministic: bool = False  # not in the reference: reproducible, reference-ordered E/B path (ION_EXT_DETERMINISTIC)
 
     def to_c(self) -> IonLbmConfig:
         c = IonLbmConfig()
@@ -126,6 +127,7 @@ class LbmConfig:
         c.ext_subgrid_ecr = int(self.ext_subgrid_ecr)
         c.mhd_lod_depth = self.mhd_lod_depth
         c.graphics_active = int(self.graphics_config.graphics_active)
+        c.deterministic = int(self.deterministic)
         c.ecr_freq, c.ecr_field_strength, c.run_steps = self.ecr_freq, self.ecr_field_strength, self.run_steps
         return c
 
@@ -139,7 +141,7 @@ class LbmConfig:
             ext_force_field=bool(c.ext_force_field), ext_magneto_hydro=bool(c.ext_magneto_hydro),
             ext_subgrid_ecr=bool(c.ext_subgrid_ecr), mhd_lod_depth=c.mhd_lod_depth, ecr_freq=c.ecr_freq,
             ecr_field_strength=c.ecr_field_strength, graphics_config=GraphicsConfig(bool(c.graphics_active)),
-            run_steps=c.run_steps)
+            run_steps=c.run_steps, deterministic=bool(c.deterministic))
 
     def make_params(self, d=0) -> capi.IonParams:
         """get_device_defines (domain.rs:736-858) for domain d; needs no GPU."""

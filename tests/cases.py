@@ -54,6 +54,8 @@ def mhd_cases():
     return [
         ("mhd_d3q19_fp32_lod3", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=32, n_z=32, nu=0.05, ext_volume_force=True,
                                       ext_magneto_hydro=True, mhd_lod_depth=3, graphics_active=True))),
+        ("mhd_d3q19_fp32_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=16, n_z=48, nu=0.05, ext_volume_force=True,
+                                      ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True))),
         ("mhd_d3q19_fp32_lod2", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=32, n_z=32, nu=0.05, ext_volume_force=True,
                                       ext_magneto_hydro=True, mhd_lod_depth=2))),
         ("mhd_d3q27_fp16c_lod1", _mhd(C(velocity_set="D3Q27", float_type="FP16C", n_x=16, n_y=16, n_z=16, nu=0.05, ext_volume_force=True,
@@ -119,7 +121,7 @@ RT = {"SRT": 0, "TRT": 1}
 FT = {"FP16S": 0, "FP16C": 1, "FP32": 2}
 
 
-def to_lbm_config(cfg):
+def to_lbm_config(cfg, deterministic=False):
     """RefConfig -> product LbmConfig (same field names as mod.rs:46-101)."""
     from ionsolver_b200 import lbm as L
     u = cfg.units
@@ -130,7 +132,7 @@ def to_lbm_config(cfg):
         f_x=cfg.f_x, f_y=cfg.f_y, f_z=cfg.f_z, ext_equilibrium_boudaries=cfg.ext_equilibrium_boudaries,
         ext_volume_force=cfg.ext_volume_force, ext_force_field=cfg.ext_force_field, ext_magneto_hydro=cfg.ext_magneto_hydro,
         ext_subgrid_ecr=cfg.ext_subgrid_ecr, mhd_lod_depth=cfg.mhd_lod_depth, ecr_freq=cfg.ecr_freq,
-        graphics_config=L.GraphicsConfig(cfg.graphics_active))
+        graphics_config=L.GraphicsConfig(cfg.graphics_active), deterministic=deterministic)
 
 
 # oracle buffer name -> product field id (include/ionsolver_b200.h enum IonField)
