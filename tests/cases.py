@@ -111,9 +111,35 @@ def fill_inputs(lbm, cfg, seed=1, smooth=False):
         if cfg.ext_force_field:
             d.f[:] = (1e-4 * rng.standard_normal(3 * n)).astype(np.float32)
         if cfg.ext_magneto_hydro:
-            d.qc[:] = (0.002 + 0.0005 * rng.standard_normal(n)).astype(np.float32)
+            d.qc[:] = (RHO_E0 + 0.002 + 0.0005 * rng.standard_normal(n)).astype(np.float32)
             d.b_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
             d.e_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
+
+
+# The reference initialises the electron gas at density 0 (initialize: calculate_f_eq(0.0, ...), quirk Q10); its first
+# stream_collide then divides by rho_e = 0 in some cells and the NaN floods every field within three steps.  The MHD
+# scenes therefore give the electron gas a finite density after initialize(), the way a user of the reference has to:
+# by writing the `ei` buffer.  Gas charge (fill_inputs) is RHO_E0 + 0.002 so that the net charge stays small.
+RHO_E0 = 0.1
+_W = {"D3Q15": [2 / 9] + [1 / 9] * 6 + [1 / 72] * 8, "D3Q19": [1 / 3] + [1 / 18] * 6 + [1 / 36] * 12,
+      "D3Q27": [8 / 27] + [2 / 27] * 6 + [1 / 54] * 12 + [1 / 216] * 8}
+
+
+def electron_gas_at_rest(ref_domain, cfg, rho_e=RHO_E0):
+    """Stored `ei` DDFs of a resting electron gas of density rho_e: DDF-shifted equilibrium f_i = w_i (rho_e - 1)."""
+    w = np.asarray(_W[cfg.velocity_set], np.float32)
+    ei = (w[:, None] * np.float32(rho_e - 1.0) * np.ones((len(w), ref_domain.g.n), np.float32)).astype(np.float32).ravel()
+    return ei if cfg.float_type == "FP32" else ref_domain.codec(ei, 0)
+
+
+def seed_electron_gas(ref_lbm, gpu_lbm=None):
+    """Call after initialize() on both sides."""
+    cfg = ref_lbm.config
+    for i, rd in enumerate(ref_lbm.domains):
+        stored = electron_gas_at_rest(rd, cfg)
+        rd.ei[:] = stored
+        if gpu_lbm is not None:
+            gpu_lbm.domains[i].write(FIELD_OF["ei"], stored)
 
 
 VS = {"D2Q9": 0, "D3Q15": 1, "D3Q19": 2, "D3Q27": 3}

@@ -26,7 +26,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import cases  # noqa: E402
 from oracle import build_ref, ref_host as rh  # noqa: E402
 
-STEPS = 4
+STEPS = 8
 
 
 def sha(a):
@@ -57,9 +57,13 @@ def run_case(cfg):
     rec = {"inputs": [{n: sha(getattr(d, n)) for n in ("rho", "u", "flags")} for d in lbm.domains]}
     lbm.initialize()
     rec["after_initialize"] = [buffers_of(d, cfg) for d in lbm.domains]
+    if cfg.ext_magneto_hydro:
+        cases.seed_electron_gas(lbm)  # see cases.RHO_E0: without it the reference NaNs out within three steps
     for _ in range(STEPS):
         lbm.do_time_step()
     rec["after_steps"] = [buffers_of(d, cfg) for d in lbm.domains]
+    nans = sum(v.get("nan", 0) for d in rec["after_steps"] for v in d.values())
+    assert nans == 0, f"NaN in the reference run: {nans}"
     rec["steps"] = STEPS
     return rec
 

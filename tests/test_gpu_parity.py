@@ -95,7 +95,9 @@ def test_mhd_single_step_parity(name, cfg, golden, gpu_lib):
     rd, gd = ref.domains[0], gpu.domains[0]
     assert rel_l2(gd.read(cases.FIELD_OF["e_dyn"]), rd.e_dyn) < TOL_EB_1STEP
     assert rel_l2(gd.read(cases.FIELD_OF["b_dyn"]), rd.b_dyn) < TOL_EB_1STEP
-    # make the inputs of the step identical (E_dyn differs in the last bit), then step once
+    # give the electron gas a finite density (cases.RHO_E0) and make the inputs of the step identical (E_dyn differs
+    # in the last bit), then step once
+    cases.seed_electron_gas(ref, gpu)
     gd.write(cases.FIELD_OF["e_dyn"], rd.e_dyn)
     gd.write(cases.FIELD_OF["b_dyn"], rd.b_dyn)
     ref.do_time_step()
@@ -128,10 +130,12 @@ def test_mhd_deterministic_mode_is_bit_exact_over_many_steps(name, cfg, golden, 
     ref.initialize()
     gpu.initialize()
     assert_bit_exact(ref, gpu, cfg, names, "after initialize")
+    cases.seed_electron_gas(ref, gpu)
     for _ in range(g["steps"]):
         ref.do_time_step()
         gpu.do_time_step()
     gpu.finish_queues()
+    assert not any(np.isnan(getattr(d, n)).any() for d in ref.domains for n in ("rho", "qc", "e_dyn"))
     assert_bit_exact(ref, gpu, cfg, names, f"after {g['steps']} steps")
     for gd, gg in zip(gpu.domains, g["after_steps"]):  # ... and to the reference's own kernels (golden vectors)
         for n in names:
@@ -156,6 +160,7 @@ def test_default_and_deterministic_e_b_agree(gpu_lib):
             cases.upload_inputs(ref, gpu)
             gpu.initialize()
             d = gpu.domains[0]
+            d.write(cases.FIELD_OF["ei"], cases.electron_gas_at_rest(ref.domains[0], cfg))
             d.write(cases.FIELD_OF["e_dyn"], ref.domains[0].e_stat)  # identical step inputs for both modes
             d.write(cases.FIELD_OF["b_dyn"], ref.domains[0].b_stat)
             gpu.do_time_step()
@@ -210,6 +215,7 @@ def test_multi_domain_mhd(name, cfg, gpu_lib):
     gpu.initialize()
     exact = ["fi", "ei", "fqi", "qc", "flags"]
     assert_bit_exact(ref, gpu, cfg, exact, "after initialize")
+    cases.seed_electron_gas(ref, gpu)
     for rd, gd in zip(ref.domains, gpu.domains):
         gd.write(cases.FIELD_OF["e_dyn"], rd.e_dyn)
         gd.write(cases.FIELD_OF["b_dyn"], rd.b_dyn)

@@ -28,6 +28,8 @@ def test_port_matches_reference_golden(name, cfg, golden):
             assert sha(getattr(d, n)) == gi[n], f"input {n} differs from the generator's: numpy RNG drift?"
     lbm.initialize()
     bad = check_against_golden(lbm, cfg, g["after_initialize"], "after initialize")
+    if cfg.ext_magneto_hydro:
+        cases.seed_electron_gas(lbm)
     for _ in range(g["steps"]):
         lbm.do_time_step()
     bad += check_against_golden(lbm, cfg, g["after_steps"], f"after {g['steps']} steps")
@@ -41,8 +43,11 @@ def test_port_matches_live_reference_build(name, cfg):
     b = rh.RefLbm(cfg, threads=1, backend="port")
     cases.fill_inputs(a, cfg, seed=5)
     cases.fill_inputs(b, cfg, seed=5)
-    a.run(3)
-    b.run(3)
+    for lbm in (a, b):
+        lbm.initialize()
+        if cfg.ext_magneto_hydro:
+            cases.seed_electron_gas(lbm)
+        lbm.run(3)
     for da, db in zip(a.domains, b.domains):
         for n in buffer_names(cfg):
             assert same_bits(getattr(da, n), getattr(db, n)), f"domain {da.g.d_i} buffer {n}"
