@@ -13,6 +13,8 @@
 //      the reference expression to ~1e-6 relative, inside the stated E/B tolerance (tests/test_gpu_parity.py).
 //   3. the near-cell loop of sim.cl:919-938 (only non-empty for depth <= 2 or N > 2^16, quirk Q4) reads Q,u
 //      directly; neighbouring threads read the same addresses, which L1 serves as broadcasts.
+#include <cstdlib>
+
 #include "lattice.cuh"
 
 namespace ion {
@@ -373,6 +375,218 @@ __global__ void __launch_bounds__(EBT_BLOCK) k_update_e_b_tiled(const __grid_con
     }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Circular packed-FP32 variant of the tiled kernel (fast path, EXACT = false only).
+//
+// Why: ncu on k_update_e_b_tiled<16,false> (profiles/r1_ncu_update_e_b.md) shows FMA pipe 54 %, issue 63 %, and the top
+// stall "no_instruction": its fully unrolled 16x16 Toeplitz tile is ~56 KB of straight-line code per source row, well
+// past the 32 KB L1.5 instruction cache.  The arithmetic floor is 9 FMA per (cell, source) pair; scalar FFMA already
+// runs at full rate on sm_100 (tests/tools/fp32_peak.cu: 3.6e13 FMA/s scalar, 3.3e13 packed), so packing does not
+// raise the FMA ceiling -- it halves the instruction count, which (a) makes the unrolled tile fit the instruction
+// cache and (b) frees issue slots for the LDS / MUFU / address work next to a saturated FMA pipe.
+//
+// Tile: a thread owns NC cells k = kbase + kl (kl = 0..NC-1, same in-block offset ox) of one x-row; a source row has
+// ND sources c.  Instead of walking the 2*ND-1 Toeplitz diagonals (ragged: 1..ND pairs each), the tile is walked
+// CIRCULARLY: step D' = 0..ND-1 pairs cell kl with source c = (kl - D') mod ND, whose true diagonal is
+// D = D' (kl >= D', "hi") or D' - ND (kl < D', "lo").  Every step then has exactly NC pairs and every (cell, source)
+// pair occurs once.  FFMA2 lanes = cells (2j, 2j+1); their sources (c, c+1 mod ND) are one aligned entry of a
+// shared-memory table that stores, for every source t of a row, the pair (S_t, S_(t+1) mod ND) as two float4
+// {q_t, q_t', wx_t, wx_t'}, {wy_t, wy_t', wz_t, wz_t'} -- two broadcast LDS.128 feed nine FFMA2 (18 pair terms).
+// r/|r|^3 enters as a scalar broadcast operand (hi or lo), or as a true (lo, hi) pair on the one lane pair per odd D'
+// that straddles the wrap.  Everything is unrolled: ND*NC/2*11 + ~2*ND*14 instructions (16 KB for ND=16, NC=8).
+// Per cell the sources are NOT visited in ascending order any more (cell kl starts at source kl and wraps), so E/B
+// differ from k_update_e_b_tiled<ND,false> by summation-order rounding (~1e-7 relative); the deterministic path
+// (EXACT) is untouched.  The own block (sim.cl:944) is removed by zeroing r/|r|^3 of its diagonal.
+// ------------------------------------------------------------------------------------------------------
+template <int NC>
+__device__ __forceinline__ void pair_get(const float2 (&e2)[NC / 2][3], const float2 (&b2)[NC / 2][3], int k, float* ek, float* bk) {
+#pragma unroll
+    for (int j = 0; j < NC / 2; j++) {
+        if (2 * j == k) { ek[0] = e2[j][0].x; ek[1] = e2[j][1].x; ek[2] = e2[j][2].x; bk[0] = b2[j][0].x; bk[1] = b2[j][1].x; bk[2] = b2[j][2].x; }
+        if (2 * j + 1 == k) { ek[0] = e2[j][0].y; ek[1] = e2[j][1].y; ek[2] = e2[j][2].y; bk[0] = b2[j][0].y; bk[1] = b2[j][1].y; bk[2] = b2[j][2].y; }
+    }
+}
+template <int NC>
+__device__ __forceinline__ void pair_put(float2 (&e2)[NC / 2][3], float2 (&b2)[NC / 2][3], int k, const float* ek, const float* bk) {
+#pragma unroll
+    for (int j = 0; j < NC / 2; j++) {
+        if (2 * j == k) { e2[j][0].x = ek[0]; e2[j][1].x = ek[1]; e2[j][2].x = ek[2]; b2[j][0].x = bk[0]; b2[j][1].x = bk[1]; b2[j][2].x = bk[2]; }
+        if (2 * j + 1 == k) { e2[j][0].y = ek[0]; e2[j][1].y = ek[1]; e2[j][2].y = ek[2]; b2[j][0].y = bk[0]; b2[j][1].y = bk[1]; b2[j][2].y = bk[2]; }
+    }
+}
+// nine FFMA2: e += q*p, b += w x p for two cells at once (same rounding sequence as accumulate_pair<false>)
+__device__ __forceinline__ void fma_pair(float2* e, float2* b, const float4 A, const float4 B, const float2 PX, const float2 PY, const float2 PZ) {
+    const float2 q = make_float2(A.x, A.y), wx = make_float2(A.z, A.w), wy = make_float2(B.x, B.y), wz = make_float2(B.z, B.w);
+    const float2 NX = make_float2(-PX.x, -PX.y), NY = make_float2(-PY.x, -PY.y), NZ = make_float2(-PZ.x, -PZ.y);
+    e[0] = __ffma2_rn(q, PX, e[0]);
+    e[1] = __ffma2_rn(q, PY, e[1]);
+    e[2] = __ffma2_rn(q, PZ, e[2]);
+    b[0] = __ffma2_rn(wy, PZ, __ffma2_rn(wz, NY, b[0]));
+    b[1] = __ffma2_rn(wz, PX, __ffma2_rn(wx, NZ, b[1]));
+    b[2] = __ffma2_rn(wx, PY, __ffma2_rn(wy, NX, b[2]));
+}
+
+// VOL = true: every (step, lane pair) re-reads its source entry with a volatile LDS.128 (2 LDS per 9 FFMA2, few registers);
+// VOL = false: the compiler may keep the whole row table (2*ND float4 = 8*ND registers) in registers across the steps.
+template <bool VOL> __device__ __forceinline__ float4 lds128(const float4* p) {
+    if (VOL) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)));
+        return v;
+    }
+    return *p;
+}
+
+template <int ND, int NC, int BLOCK, bool VOL>
+__global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
+                                                                const uint32_t n_foreign) {
+    static_assert(ND % NC == 0 && NC % 2 == 0, "cells per thread");
+    constexpr int PARTS = ND / NC;
+    extern __shared__ float4 s_pair[];  // slot t -> {q_t, q_t', wx_t, wx_t'}, {wy_t, wy_t', wz_t, wz_t'}; t' = next source of the row, cyclic
+    const uint32_t fine = (uint32_t)ND * ND * ND;
+    const uint32_t lo = a.n_lod_own >= fine ? a.n_lod_own - fine : 0u;  // sim.cl:943
+    const uint32_t cnt = a.n_lod_own - lo;
+    for (uint32_t k = threadIdx.x; k < cnt; k += BLOCK) {
+        const uint32_t d = lo + k;
+        const uint32_t dn = (d % ND == ND - 1u) ? d - (ND - 1u) : d + 1u;  // cyclic successor inside the row
+        const float4 v0 = __ldg(reinterpret_cast<const float4*>(a.QU_lod) + d);
+        float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (dn >= lo && dn < a.n_lod_own) v1 = __ldg(reinterpret_cast<const float4*>(a.QU_lod) + dn);
+        s_pair[2u * k] = make_float4(v0.x, v1.x, v0.y * v0.x, v1.y * v1.x);
+        s_pair[2u * k + 1u] = make_float4(v0.z * v0.x, v1.z * v1.x, v0.w * v0.x, v1.w * v1.x);
+    }
+    __syncthreads();
+    const uint32_t dsx = a.nx / ND, dsy = a.ny / ND, dsz = a.nz / ND;
+    const uint32_t m = blockIdx.x * BLOCK + threadIdx.x;  // (ox, part, y) of this thread, z = blockIdx.y
+    if (m >= dsx * PARTS * a.ny) return;
+    const uint32_t ox = m % dsx, part = (m / dsx) % PARTS, y = m / (dsx * PARTS), z = blockIdx.y;
+    const uint32_t kbase = part * NC;
+    const uint64_t N = a.N;
+    const uint32_t row0 = y * a.nx + z * a.nx * a.ny;
+    const float fy = (float)y, fz = (float)z;
+    const float dsxf = (float)dsx, dsyf = (float)dsy, dszf = (float)dsz;
+    const uint32_t self_row = y / dsy + (z / dsz) * ND;
+
+    float2 e2[NC / 2][3], b2[NC / 2][3];
+#pragma unroll
+    for (int j = 0; j < NC / 2; j++)
+#pragma unroll
+        for (int c = 0; c < 3; c++) { e2[j][c] = make_float2(0.f, 0.f); b2[j][c] = make_float2(0.f, 0.f); }
+
+    // ---- close distance (sim.cl:907-938), as in k_update_e_b_tiled ----
+    {
+        const uint32_t sh = 1u << ND;
+        const uint32_t nsx = a.nx / sh > 1u ? a.nx / sh : 1u, nsy = a.ny / sh > 1u ? a.ny / sh : 1u, nsz = a.nz / sh > 1u ? a.nz / sh : 1u;
+        if (nsx * nsy * nsz > 1u) {
+            for (int kl = 0; kl < NC; kl++) {
+                const uint32_t x = (kbase + (uint32_t)kl) * dsx + ox, n = row0 + x;
+                const uint32_t xu = min((x / nsx) * nsx + nsx, a.dx > 1u ? a.nx - 1u : a.nx);
+                const uint32_t yu = min((y / nsy) * nsy + nsy, a.dy > 1u ? a.ny - 1u : a.ny);
+                const uint32_t zu = min((z / nsz) * nsz + nsz, a.dz > 1u ? a.nz - 1u : a.nz);
+                float ek[3] = {0.f, 0.f, 0.f}, bk[3] = {0.f, 0.f, 0.f};
+                for (uint32_t xc = max((x / nsx) * nsx, a.dx > 1u ? 1u : 0u); xc < xu; xc++)
+                    for (uint32_t yc = max((y / nsy) * nsy, a.dy > 1u ? 1u : 0u); yc < yu; yc++)
+                        for (uint32_t zc = max((z / nsz) * nsz, a.dz > 1u ? 1u : 0u); zc < zu; zc++) {
+                            const uint32_t nc = xc + (yc + zc * a.ny) * a.nx;
+                            if (nc == n) continue;
+                            const float qc = a.Q[nc];
+                            if (qc == 0.0f) continue;
+                            const float4 s = make_float4(qc, a.u[nc] * qc, a.u[N + nc] * qc, a.u[2ull * N + nc] * qc);
+                            float px, py, pz;
+                            pre_field<false>((float)x - (float)xc, fy - (float)yc, fz - (float)zc, px, py, pz);
+                            accumulate_pair<false>(ek, bk, s, px, py, pz, false);
+                        }
+                pair_put<NC>(e2, b2, kl, ek, bk);
+            }
+        }
+    }
+
+    // ---- own LODs (sim.cl:940-955) ----
+    const float rx0 = (float)(kbase * dsx + ox) - 0.5f * dsxf;  // r_x of cell kl = 0 against source c = 0
+    const uint32_t row_lo = lo / ND, row_hi = (a.n_lod_own + ND - 1) / ND;
+    for (uint32_t row = row_lo; row < row_hi; row++) {
+        const uint32_t cy = row % ND, cz = row / ND;
+        const float ry = fy - ((float)cy * dsyf + 0.5f * dsyf);
+        const float rz = fz - ((float)cz * dszf + 0.5f * dszf);
+        const bool is_self = row == self_row;
+        const int d0 = (int)(row * ND) - (int)lo;
+        if (d0 < 0 || d0 + ND > (int)cnt) {  // ragged first / last row: only slots inside [0, cnt) exist
+            for (int kl = 0; kl < NC; kl++) {
+                float ek[3], bk[3];
+                pair_get<NC>(e2, b2, kl, ek, bk);
+                const int k = (int)kbase + kl;
+                for (int cx = 0; cx < ND; cx++) {
+                    const int slot = d0 + cx;
+                    if (slot < 0 || slot >= (int)cnt || (is_self && cx == k)) continue;
+                    const float4 A = s_pair[2 * slot], B = s_pair[2 * slot + 1];
+                    float px, py, pz;
+                    pre_field<false>((float)(kl - cx) * dsxf + rx0, ry, rz, px, py, pz);
+                    accumulate_pair<false>(ek, bk, make_float4(A.x, A.z, B.x, B.z), px, py, pz, false);
+                }
+                pair_put<NC>(e2, b2, kl, ek, bk);
+            }
+            continue;
+        }
+        const float4* __restrict__ srow = s_pair + 2 * d0;
+        const int self_dl = is_self ? -(int)kbase : 0x7fffffff;  // local diagonal of the own block (true diagonal 0)
+#pragma unroll
+        for (int Dp = 0; Dp < ND; Dp++) {
+            // hi: cells kl >= D' on local diagonal D'; lo: cells kl < D' on local diagonal D' - ND
+            float hx = 0.f, hy = 0.f, hz = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
+            if (Dp < NC) {
+                pre_field<false>((float)Dp * dsxf + rx0, ry, rz, hx, hy, hz);
+                if (Dp == self_dl) hx = hy = hz = 0.0f;
+            }
+            if (Dp > 0) {
+                pre_field<false>((float)(Dp - ND) * dsxf + rx0, ry, rz, lx, ly, lz);
+                if (Dp - ND == self_dl) lx = ly = lz = 0.0f;
+            }
+#pragma unroll
+            for (int j = 0; j < NC / 2; j++) {
+                const int t = ((2 * j - Dp) % ND + ND) % ND;  // source of lane .x; lane .y uses its cyclic successor
+                const float4 A = lds128<VOL>(srow + 2 * t), B = lds128<VOL>(srow + 2 * t + 1);
+                const bool xh = 2 * j >= Dp, yh = 2 * j + 1 >= Dp;
+                fma_pair(e2[j], b2[j], A, B, make_float2(xh ? hx : lx, yh ? hx : lx), make_float2(xh ? hy : ly, yh ? hy : ly),
+                         make_float2(xh ? hz : lz, yh ? hz : lz));
+            }
+        }
+    }
+
+    // ---- foreign-domain LODs (sim.cl:957-983) ----
+    for (uint32_t f = 0; f < n_foreign; f++) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(foreign + f));
+        float4 s = __ldg(reinterpret_cast<const float4*>(foreign + f) + 1);
+        s = make_float4(c.w, s.x * c.w, s.y * c.w, s.z * c.w);
+        const float ry = fy - c.y, rz = fz - c.z;
+#pragma unroll
+        for (int j = 0; j < NC / 2; j++) {
+            float p0x, p0y, p0z, p1x, p1y, p1z;
+            pre_field<false>((float)((kbase + (uint32_t)(2 * j)) * dsx + ox) - c.x, ry, rz, p0x, p0y, p0z);
+            pre_field<false>((float)((kbase + (uint32_t)(2 * j + 1)) * dsx + ox) - c.x, ry, rz, p1x, p1y, p1z);
+            fma_pair(e2[j], b2[j], make_float4(s.x, s.x, s.y, s.y), make_float4(s.z, s.z, s.w, s.w), make_float2(p0x, p1x), make_float2(p0y, p1y),
+                     make_float2(p0z, p1z));
+        }
+    }
+
+    // ---- sim.cl:986-992 ----
+#pragma unroll
+    for (int kl = 0; kl < NC; kl++) {
+        const uint32_t x = (kbase + (uint32_t)kl) * dsx + ox;
+        const uint32_t n = row0 + x;
+        if (is_halo(a, x, y, z)) continue;
+        if ((a.flags[n] & ION_TYPE_BO) == ION_TYPE_S) continue;
+        const int j = kl / 2;
+        const float ex = (kl & 1) ? e2[j][0].y : e2[j][0].x, ey = (kl & 1) ? e2[j][1].y : e2[j][1].x, ez = (kl & 1) ? e2[j][2].y : e2[j][2].x;
+        const float bx = (kl & 1) ? b2[j][0].y : b2[j][0].x, by = (kl & 1) ? b2[j][1].y : b2[j][1].x, bz = (kl & 1) ? b2[j][2].y : b2[j][2].x;
+        a.E_dyn[n] = a.E_stat[n] + a.ke * ex;
+        a.E_dyn[N + n] = a.E_stat[N + n] + a.ke * ey;
+        a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n] + a.ke * ez;
+        a.B_dyn[n] = a.B_stat[n] + a.kmu * bx;
+        a.B_dyn[N + n] = a.B_stat[N + n] + a.kmu * by;
+        a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n] + a.kmu * bz;
+    }
+}
+
 // Deterministic LOD deposit (ION_EXT_DETERMINISTIC): the reference adds every cell's (Q, u/cells) to its finest-level LOD
 // entry with float atomics (sim.cl:666-677), i.e. in execution order.  Here one thread per (entry, component) walks the
 // cells of its block in ascending cell index -- the order of a sequential run of the reference kernel -- so the sums
@@ -437,6 +651,19 @@ __global__ void k_lod_gather(float* __restrict__ lods, uint32_t depth) {
 }
 
 // ---- launchers used by api.cu ----
+template <int ND, int NC, int BLOCK, bool VOL>
+static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s) {
+    const size_t smem = (size_t)own * 2 * sizeof(float4);
+    if (smem > 48u * 1024u) {
+        cudaError_t e = cudaFuncSetAttribute(k_update_e_b_pair<ND, NC, BLOCK, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * fine_bytes(ND)));
+        if (e != cudaSuccess) return e;
+    }
+    const uint32_t threads_per_plane = (a.nx / ND) * (ND / NC) * a.ny;
+    const dim3 grid((threads_per_plane + BLOCK - 1) / BLOCK, a.nz);
+    k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own);
+    return cudaGetLastError();
+}
+
 template <int ND, bool EXACT>
 static cudaError_t launch_tiled(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s) {
     const size_t smem = (size_t)own * sizeof(float4);
@@ -460,8 +687,19 @@ cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_
     const uint32_t fine = nd * nd * nd;
     const uint32_t own = a.n_lod_own >= fine ? fine : a.n_lod_own;
     if ((a.lod_depth == 3u || a.lod_depth == 4u) && a.nx % nd == 0u && a.n_lod_own >= fine && a.ny >= nd && a.nz >= nd) {
-        if (a.lod_depth == 4u) return exact ? launch_tiled<16, true>(a, src, own, count, s) : launch_tiled<16, false>(a, src, own, count, s);
-        return exact ? launch_tiled<8, true>(a, src, own, count, s) : launch_tiled<8, false>(a, src, own, count, s);
+        // fast path: circular packed-FFMA2 kernel.  ION_EB_VARIANT (A/B timing only): 0 = scalar tiled kernel,
+        // 1 = 8 cells/thread, row table in registers (default), 2 = 16 cells/thread + volatile LDS, 3 = 8 cells/thread + volatile
+        // LDS at 512 threads, 4 = 16 cells/thread, row table in registers
+        static const int variant = getenv("ION_EB_VARIANT") ? atoi(getenv("ION_EB_VARIANT")) : 1;
+        if (exact) return a.lod_depth == 4u ? launch_tiled<16, true>(a, src, own, count, s) : launch_tiled<8, true>(a, src, own, count, s);
+        if (variant == 0) return a.lod_depth == 4u ? launch_tiled<16, false>(a, src, own, count, s) : launch_tiled<8, false>(a, src, own, count, s);
+        if (a.lod_depth == 4u) {
+            if (variant == 2) return launch_pair<16, 16, 256, true>(a, src, own, count, s);
+            if (variant == 3) return launch_pair<16, 8, 512, true>(a, src, own, count, s);
+            if (variant == 4) return launch_pair<16, 16, 256, false>(a, src, own, count, s);
+            return launch_pair<16, 8, 256, false>(a, src, own, count, s);
+        }
+        return variant == 2 || variant == 3 ? launch_pair<8, 8, 256, true>(a, src, own, count, s) : launch_pair<8, 8, 256, false>(a, src, own, count, s);
     }
     unsigned b = ((a.nx + 31u) / 32u) * 32u;
     if (b > (unsigned)EB_BLOCK) b = EB_BLOCK;
