@@ -529,25 +529,25 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
         }
         const float4* __restrict__ srow = s_pair + 2 * d0;
         const int self_dl = is_self ? -(int)kbase : 0x7fffffff;  // local diagonal of the own block (true diagonal 0)
+        const float ryz2 = fmaf(ry, ry, rz * rz);
 #pragma unroll
         for (int Dp = 0; Dp < ND; Dp++) {
-            // hi: cells kl >= D' on local diagonal D'; lo: cells kl < D' on local diagonal D' - ND
-            float hx = 0.f, hy = 0.f, hz = 0.f, lx = 0.f, ly = 0.f, lz = 0.f;
-            if (Dp < NC) {
-                pre_field<false>((float)Dp * dsxf + rx0, ry, rz, hx, hy, hz);
-                if (Dp == self_dl) hx = hy = hz = 0.0f;
-            }
-            if (Dp > 0) {
-                pre_field<false>((float)(Dp - ND) * dsxf + rx0, ry, rz, lx, ly, lz);
-                if (Dp - ND == self_dl) lx = ly = lz = 0.0f;
-            }
+            // hi (.y): cells kl >= D' on local diagonal D'; lo (.x): cells kl < D' on local diagonal D' - ND.  Both r/|r|^3
+            // vectors are evaluated together with packed FP32 (same roundings as pre_field<false>).
+            const float2 rx = make_float2((float)(Dp - ND) * dsxf + rx0, (float)Dp * dsxf + rx0);
+            const float2 r2 = __ffma2_rn(rx, rx, make_float2(ryz2, ryz2));
+            const float2 ri = make_float2(r2.x > 0.0f ? rsqrtf(r2.x) : 0.0f, r2.y > 0.0f ? rsqrtf(r2.y) : 0.0f);
+            float2 ri3 = __fmul2_rn(__fmul2_rn(ri, ri), ri);
+            if (Dp - ND == self_dl) ri3.x = 0.0f;  // the own block contributes nothing (sim.cl:944)
+            if (Dp == self_dl) ri3.y = 0.0f;
+            const float2 px = __fmul2_rn(rx, ri3), py = __fmul2_rn(make_float2(ry, ry), ri3), pz = __fmul2_rn(make_float2(rz, rz), ri3);
 #pragma unroll
             for (int j = 0; j < NC / 2; j++) {
                 const int t = ((2 * j - Dp) % ND + ND) % ND;  // source of lane .x; lane .y uses its cyclic successor
                 const float4 A = lds128<VOL>(srow + 2 * t), B = lds128<VOL>(srow + 2 * t + 1);
                 const bool xh = 2 * j >= Dp, yh = 2 * j + 1 >= Dp;
-                fma_pair(e2[j], b2[j], A, B, make_float2(xh ? hx : lx, yh ? hx : lx), make_float2(xh ? hy : ly, yh ? hy : ly),
-                         make_float2(xh ? hz : lz, yh ? hz : lz));
+                fma_pair(e2[j], b2[j], A, B, make_float2(xh ? px.y : px.x, yh ? px.y : px.x), make_float2(xh ? py.y : py.x, yh ? py.y : py.x),
+                         make_float2(xh ? pz.y : pz.x, yh ? pz.y : pz.x));
             }
         }
     }
@@ -687,17 +687,23 @@ cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_
     const uint32_t fine = nd * nd * nd;
     const uint32_t own = a.n_lod_own >= fine ? fine : a.n_lod_own;
     if ((a.lod_depth == 3u || a.lod_depth == 4u) && a.nx % nd == 0u && a.n_lod_own >= fine && a.ny >= nd && a.nz >= nd) {
-        // fast path: circular packed-FFMA2 kernel.  ION_EB_VARIANT (A/B timing only): 0 = scalar tiled kernel,
-        // 1 = 8 cells/thread, row table in registers (default), 2 = 16 cells/thread + volatile LDS, 3 = 8 cells/thread + volatile
-        // LDS at 512 threads, 4 = 16 cells/thread, row table in registers
-        static const int variant = getenv("ION_EB_VARIANT") ? atoi(getenv("ION_EB_VARIANT")) : 1;
+        // Fast path.  Depth 4 (16^3 sources): circular packed-FFMA2 kernel, 16 cells per thread (26.2 ms at 256^3 vs 36.3 ms
+        // for the scalar tiled kernel, whose unrolled tile overflows the instruction cache).  Depth 3 (8^3 sources): the
+        // scalar tiled kernel -- its 8x8 tile is 13 KB of code and runs at 16 warps/SM (4.8 ms vs 6.1 ms packed).
+        // ION_EB_VARIANT overrides for A/B timing: 0 scalar tiled, 1 = 8 cells/thread with the row table in registers,
+        // 2 = 16 cells/thread + volatile LDS, 3 = 8 cells/thread + volatile LDS at 512 threads, 4 = 16 cells/thread, row table
+        // in registers.
         if (exact) return a.lod_depth == 4u ? launch_tiled<16, true>(a, src, own, count, s) : launch_tiled<8, true>(a, src, own, count, s);
-        if (variant == 0) return a.lod_depth == 4u ? launch_tiled<16, false>(a, src, own, count, s) : launch_tiled<8, false>(a, src, own, count, s);
+        static const int variant = getenv("ION_EB_VARIANT") ? atoi(getenv("ION_EB_VARIANT")) : -1;
+        if (variant == 0 || (variant < 0 && a.lod_depth == 3u))
+            return a.lod_depth == 4u ? launch_tiled<16, false>(a, src, own, count, s) : launch_tiled<8, false>(a, src, own, count, s);
         if (a.lod_depth == 4u) {
-            if (variant == 2) return launch_pair<16, 16, 256, true>(a, src, own, count, s);
+            if (variant == 1) return launch_pair<16, 8, 256, false>(a, src, own, count, s);
             if (variant == 3) return launch_pair<16, 8, 512, true>(a, src, own, count, s);
             if (variant == 4) return launch_pair<16, 16, 256, false>(a, src, own, count, s);
-            return launch_pair<16, 8, 256, false>(a, src, own, count, s);
+            if (variant == 5) return launch_pair<16, 16, 384, true>(a, src, own, count, s);
+            if (variant == 6) return launch_pair<16, 8, 384, true>(a, src, own, count, s);
+            return launch_pair<16, 16, 256, true>(a, src, own, count, s);
         }
         return variant == 2 || variant == 3 ? launch_pair<8, 8, 256, true>(a, src, own, count, s) : launch_pair<8, 8, 256, false>(a, src, own, count, s);
     }
