@@ -181,6 +181,17 @@ ION_API int ion_exchange_transfer(ion_domain_t* d, ion_domain_t* dp, size_t byte
  * [src_entry, src_entry+entries) of `src` to entry `dst_entry` of `dst` (entries are 4 floats) */
 ION_API int ion_copy_lods(ion_domain_t* dst, uint32_t dst_entry, ion_domain_t* src, uint32_t src_entry, uint32_t entries);
 
+/* exchange plan (pure host arithmetic, no GPU needed; used by ion_exchange_transfer's callers, ion_comm_exchange_lods and
+ * the host layer, and testable on CPU):
+ *   ion_neighbor_domains   ring neighbours of domain d along `axis` (0,1,2): dp = +1 (receives d's transfer_p as its
+ *                          transfer_m), dm = -1, periodic (mod.rs:386-404)
+ *   ion_lod_exchange_plan  what foreign domain dc contributes to the domain described by `p` (mod.rs:448-465): entries
+ *                          [src_entry, src_entry+entries) of dc's own pyramid (level max(0, depth - Chebyshev distance))
+ *                          land at entry dst_entry of p's QU_lod (running offset after n_lod_own, ascending dc, self skipped).
+ *                          dc == p->di yields entries = 0. */
+ION_API int ion_neighbor_domains(uint32_t d_x, uint32_t d_y, uint32_t d_z, uint32_t d, uint32_t axis, uint32_t* dp, uint32_t* dm);
+ION_API int ion_lod_exchange_plan(const IonParams* p, uint32_t dc, uint32_t* src_entry, uint32_t* entries, uint32_t* dst_entry);
+
 typedef struct ion_comm ion_comm_t;
 #define ION_COMM_ID_BYTES 128
 ION_API int ion_comm_unique_id(uint8_t id[ION_COMM_ID_BYTES]); /* rank 0 creates, the launcher broadcasts (torch.distributed) */

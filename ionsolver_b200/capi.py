@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libionsolver_b200.so")
+LIB_PATH = os.environ.get("ION_LIB") or os.path.join(_HERE, "libionsolver_b200.so")  # ION_LIB: A/B builds of the same library
 
 ION_ABI_VERSION = 1
 # enum IonVelocitySet / IonRelaxationTime / IonFloatType (wire values of src/lbm/types.rs)
@@ -46,7 +46,7 @@ SYMBOLS = [
     "ion_enqueue_precompute_e", "ion_enqueue_precompute_e_ecr", "ion_domain_set_ecr_freq", "ion_finish",
     "ion_kernel_launch_count", "ion_domain_stream",
     "ion_exchange_transfer", "ion_copy_lods", "ion_comm_unique_id", "ion_comm_create", "ion_comm_destroy",
-    "ion_comm_exchange_transfer", "ion_comm_exchange_lods",
+    "ion_comm_exchange_transfer", "ion_comm_exchange_lods", "ion_neighbor_domains", "ion_lod_exchange_plan",
 ]
 # every symbol include/ionsolver_b200_host.h declares
 HOST_SYMBOLS = [
@@ -155,6 +155,9 @@ def load() -> ctypes.CDLL:
     L.ion_comm_destroy.argtypes = [c.c_void_p]
     L.ion_comm_exchange_transfer.argtypes = [c.c_void_p, D, c.c_int, c.c_int, c.c_size_t]
     L.ion_comm_exchange_lods.argtypes = [c.c_void_p, D]
+    U32P = c.POINTER(c.c_uint32)
+    L.ion_neighbor_domains.argtypes = [c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, U32P, U32P]
+    L.ion_lod_exchange_plan.argtypes = [c.POINTER(IonParams), c.c_uint32, U32P, U32P, U32P]
     # ---- host layer (include/ionsolver_b200_host.h) ----
     CFG = c.POINTER(IonLbmConfig)
     H = c.c_void_p
@@ -322,3 +325,17 @@ class Domain:
 
     def finish(self):
         check(self.lib.ion_finish(self.handle))
+
+
+def neighbor_domains(d_x, d_y, d_z, d, axis):
+    """(dp, dm): ring neighbours of domain d along axis (ion_neighbor_domains; mod.rs:386-404).  Needs no GPU."""
+    dp, dm = ctypes.c_uint32(), ctypes.c_uint32()
+    check(load().ion_neighbor_domains(d_x, d_y, d_z, d, axis, ctypes.byref(dp), ctypes.byref(dm)))
+    return dp.value, dm.value
+
+
+def lod_exchange_plan(params: IonParams, dc):
+    """(src_entry, entries, dst_entry) of foreign domain dc for the domain described by params (mod.rs:448-465)."""
+    a, b, c_ = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    check(load().ion_lod_exchange_plan(ctypes.byref(params), dc, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c_)))
+    return a.value, b.value, c_.value

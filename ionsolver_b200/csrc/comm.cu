@@ -127,6 +127,44 @@ int ion_copy_lods(ion_domain_t* dst, uint32_t dst_entry, ion_domain_t* src, uint
     return ion_buffer_copy(dst, ION_FIELD_QU_LOD, (size_t)dst_entry * 16, src, ION_FIELD_QU_LOD, (size_t)src_entry * 16, (size_t)entries * 16);
 }
 
+int ion_neighbor_domains(uint32_t d_x, uint32_t d_y, uint32_t d_z, uint32_t d, uint32_t axis, uint32_t* dp, uint32_t* dm) {
+    if (!dp || !dm) return fail(ION_ERR_INVALID, "NULL argument");
+    if (!d_x || !d_y || !d_z || d >= d_x * d_y * d_z || axis > 2) return fail(ION_ERR_INVALID, "domain %u / axis %u out of range", d, axis);
+    const uint32_t x = (d % (d_x * d_y)) % d_x, y = (d % (d_x * d_y)) / d_x, z = d / (d_x * d_y);  // mod.rs:189-191
+    if (axis == 0) { *dp = ((x + 1) % d_x) + (y + z * d_y) * d_x; *dm = ((x + d_x - 1) % d_x) + (y + z * d_y) * d_x; }
+    else if (axis == 1) { *dp = x + (((y + 1) % d_y) + z * d_y) * d_x; *dm = x + (((y + d_y - 1) % d_y) + z * d_y) * d_x; }
+    else { *dp = x + (y + ((z + 1) % d_z) * d_y) * d_x; *dm = x + (y + ((z + d_z - 1) % d_z) * d_y) * d_x; }
+    return ION_OK;
+}
+
+int ion_lod_exchange_plan(const IonParams* p, uint32_t dc, uint32_t* src_entry, uint32_t* entries, uint32_t* dst_entry) {
+    if (!p || !src_entry || !entries || !dst_entry) return fail(ION_ERR_INVALID, "NULL argument");
+    const uint32_t dxy = p->dx * p->dy, dn = dxy * p->dz;
+    if (!dn || dc >= dn || p->di >= dn) return fail(ION_ERR_INVALID, "domain %u out of range", dc);
+    const int x = (int)((p->di % dxy) % p->dx), y = (int)((p->di % dxy) / p->dx), z = (int)(p->di / dxy);
+    const uint32_t dim = p->velocity_set == ION_D2Q9 ? 2u : 3u;
+    auto level_start = [&](int depth) {  // get_offset(depth - 1), mod.rs:441-445
+        uint32_t cnt = 0;
+        for (int i = 0; i < depth; i++) { uint32_t s = 1; for (uint32_t k = 0; k < dim; k++) s *= 1u << i; cnt += s; }
+        return cnt;
+    };
+    uint32_t offset = p->n_lod_own;
+    *src_entry = *entries = 0;
+    *dst_entry = offset;
+    for (uint32_t c = 0; c <= dc; c++) {
+        if (c == p->di) continue;
+        const int fx = (int)((c % dxy) % p->dx), fy = (int)((c % dxy) / p->dx), fz = (int)(c / dxy);
+        int dist = abs(z - fz);
+        if (abs(y - fy) > dist) dist = abs(y - fy);
+        if (abs(x - fx) > dist) dist = abs(x - fx);
+        const int depth = (int)p->lod_depth - dist > 0 ? (int)p->lod_depth - dist : 0;
+        const uint32_t rs = level_start(depth), re = level_start(depth + 1);
+        if (c == dc) { *src_entry = rs; *entries = re - rs; *dst_entry = offset; }
+        offset += re - rs;
+    }
+    return ION_OK;
+}
+
 int ion_comm_unique_id(uint8_t id[ION_COMM_ID_BYTES]) {
     static_assert(sizeof(ncclUniqueId) == ION_COMM_ID_BYTES, "ncclUniqueId size");
     if (!id) return fail(ION_ERR_INVALID, "NULL id");
@@ -200,28 +238,15 @@ int ion_comm_exchange_lods(ion_comm_t* c, ion_domain_t* d) {
     const size_t own = (size_t)p.n_lod_own * 4;  // floats
     if (!d->lod_gather) ION_CUDA(cudaMalloc((void**)&d->lod_gather, own * sizeof(float) * c->world));
     ION_NCCL(g_nccl.AllGather(d->buf[ION_FIELD_QU_LOD], d->lod_gather, own, ncclFloat, c->comm, d->stream));
-    // level selection, mod.rs:448-465: foreign domain dc contributes level max(0, depth - dist), appended in
-    // ascending dc after the own pyramid
-    const uint32_t dxy = p.dx * p.dy;
-    const int x = (int)((p.di % dxy) % p.dx), y = (int)((p.di % dxy) / p.dx), z = (int)(p.di / dxy);
-    const uint32_t dim = p.velocity_set == ION_D2Q9 ? 2u : 3u;
-    auto level_start = [&](int depth) {  // get_offset(depth - 1), mod.rs:441-445
-        size_t cnt = 0;
-        for (int i = 0; i < depth; i++) { size_t s = 1; for (uint32_t k = 0; k < dim; k++) s *= (size_t)1 << i; cnt += s; }
-        return cnt;
-    };
-    size_t offset = p.n_lod_own;
-    for (uint32_t dc = 0; dc < dxy * p.dz; dc++) {
-        if (dc == p.di) continue;
-        const int fx = (int)((dc % dxy) % p.dx), fy = (int)((dc % dxy) / p.dx), fz = (int)(dc / dxy);
-        int dist = abs(z - fz);
-        if (abs(y - fy) > dist) dist = abs(y - fy);
-        if (abs(x - fx) > dist) dist = abs(x - fx);
-        const int depth = (int)p.lod_depth - dist > 0 ? (int)p.lod_depth - dist : 0;
-        const size_t rs = level_start(depth), re = level_start(depth + 1);
-        ION_CUDA(cudaMemcpyAsync((float*)d->buf[ION_FIELD_QU_LOD] + offset * 4, d->lod_gather + (size_t)dc * own + rs * 4,
-                                 (re - rs) * 16, cudaMemcpyDeviceToDevice, d->stream));
-        offset += re - rs;
+    // level selection, mod.rs:448-465 (ion_lod_exchange_plan): foreign domain dc contributes level max(0, depth - dist),
+    // appended in ascending dc after the own pyramid
+    for (uint32_t dc = 0; dc < p.dx * p.dy * p.dz; dc++) {
+        uint32_t src = 0, cnt = 0, dst = 0;
+        int r = ion_lod_exchange_plan(&p, dc, &src, &cnt, &dst);
+        if (r) return r;
+        if (!cnt) continue;
+        ION_CUDA(cudaMemcpyAsync((float*)d->buf[ION_FIELD_QU_LOD] + (size_t)dst * 4, d->lod_gather + (size_t)dc * own + (size_t)src * 4,
+                                 (size_t)cnt * 16, cudaMemcpyDeviceToDevice, d->stream));
     }
     return ION_OK;
 }

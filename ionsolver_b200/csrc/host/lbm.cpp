@@ -400,11 +400,8 @@ void Lbm::communicate_field(TransferField field, size_t bytes_per_cell) {  // mo
         // the reference synchronises every queue here and swaps host vectors; the device-resident exchange is
         // ordered with events / NCCL stream semantics instead
         for (uint32_t d = 0; d < d_n; d++) {
-            const uint32_t x = (d % (d_x * d_y)) % d_x, y = (d % (d_x * d_y)) / d_x, z = d / (d_x * d_y);
-            uint32_t dp, dm;
-            if (axis == 0) { dp = ((x + 1) % d_x) + (y + z * d_y) * d_x; dm = ((x + d_x - 1) % d_x) + (y + z * d_y) * d_x; }
-            else if (axis == 1) { dp = x + (((y + 1) % d_y) + z * d_y) * d_x; dm = x + (((y + d_y - 1) % d_y) + z * d_y) * d_x; }
-            else { dp = x + (y + ((z + 1) % d_z) * d_y) * d_x; dm = x + (y + ((z + d_z - 1) % d_z) * d_y) * d_x; }
+            uint32_t dp, dm;  // ring neighbours, mod.rs:386-404
+            check(ion_neighbor_domains(d_x, d_y, d_z, d, axis, &dp, &dm));
             if (world == 1) {
                 const size_t bytes = domains[d].get_area(axis) * bytes_per_cell;
                 check(ion_exchange_transfer(domains[d].dev, domains[dp].dev, bytes));
@@ -428,26 +425,11 @@ void Lbm::communicate_qu_lods() {  // mod.rs:436-468
         check(ion_comm_exchange_lods(comm, domains[0].dev));
         return;
     }
-    uint8_t dimensions, vs, tr;
-    get_set_values(config.velocity_set, dimensions, vs, tr);
-    auto get_offset = [&](int depth) {
-        size_t c = 0;
-        for (int i = 0; i <= depth; i++) c += ipow((size_t)1 << i, dimensions);
-        return c;
-    };
     for (uint32_t d = 0; d < d_n; d++) {
-        uint32_t x, y, z;
-        get_coordinates_sl(d, config.d_x, config.d_y, x, y, z);
-        size_t offset = domains[d].n_lod_own;
         for (uint32_t dc = 0; dc < d_n; dc++) {
-            if (d == dc) continue;
-            uint32_t dx, dy, dz;
-            get_coordinates_sl(dc, config.d_x, config.d_y, dx, dy, dz);
-            const int dist = std::max(std::abs((int)z - (int)dz), std::max(std::abs((int)y - (int)dy), std::abs((int)x - (int)dx)));
-            const int depth = std::max(0, (int)config.mhd_lod_depth - dist);
-            const size_t range_s = get_offset(depth - 1), range_e = get_offset(depth);
-            check(ion_copy_lods(domains[d].dev, (uint32_t)offset, domains[dc].dev, (uint32_t)range_s, (uint32_t)(range_e - range_s)));
-            offset += range_e - range_s;
+            uint32_t src = 0, cnt = 0, dst = 0;  // which pyramid level of dc lands where in d's QU_lod (mod.rs:448-465)
+            check(ion_lod_exchange_plan(&domains[d].params, dc, &src, &cnt, &dst));
+            if (cnt) check(ion_copy_lods(domains[d].dev, dst, domains[dc].dev, src, cnt));
         }
     }
 }

@@ -208,26 +208,45 @@ __device__ __forceinline__ uint32_t neighbor7(const Cell& c, int i) {
 // SoA layout i*N+n (index_f, sim.cl:152-154).  Every (cell, slot) address is read and written by exactly one
 // thread per step, so the update is race-free without a second DDF copy.
 // ------------------------------------------------------------------------------------------------------
+// DDF accesses.  ION_DDF_HINT selects the cache operator (build-time experiment switch):
+// 0 = default (ld.global / st.global), 1 = streaming (ld.global.cs / st.global.cs: evict-first in L1/L2)
+#ifndef ION_DDF_HINT
+#define ION_DDF_HINT 0
+#endif
+template <typename S> __device__ __forceinline__ S ddf_ld(const S* p) {
+#if ION_DDF_HINT == 1
+    return __ldcs(p);
+#else
+    return *p;
+#endif
+}
+template <typename S> __device__ __forceinline__ void ddf_st(S* p, S v) {
+#if ION_DDF_HINT == 1
+    __stcs(p, v);
+#else
+    *p = v;
+#endif
+}
 template <int FP, int QQ, typename NB>
 __device__ __forceinline__ void ep_load(float* f, const void* buf, uint64_t N, uint32_t n, uint64_t todd, NB nb) {
     typedef typename Codec<FP>::store_t S;
     const S* p = reinterpret_cast<const S*>(buf);
-    f[0] = Codec<FP>::dec(p[n]);
+    f[0] = Codec<FP>::dec(ddf_ld(p + n));
 #pragma unroll
     for (int i = 1; i < QQ; i += 2) {
-        f[i] = Codec<FP>::dec(p[(uint64_t)(i + 1 - (int)todd) * N + n]);          // t odd ? i : i+1
-        f[i + 1] = Codec<FP>::dec(p[(uint64_t)(i + (int)todd) * N + nb(i)]);      // t odd ? i+1 : i
+        f[i] = Codec<FP>::dec(ddf_ld(p + ((uint64_t)(i + 1 - (int)todd) * N + n)));          // t odd ? i : i+1
+        f[i + 1] = Codec<FP>::dec(ddf_ld(p + ((uint64_t)(i + (int)todd) * N + nb(i))));      // t odd ? i+1 : i
     }
 }
 template <int FP, int QQ, typename NB>
 __device__ __forceinline__ void ep_store(const float* f, void* buf, uint64_t N, uint32_t n, uint64_t todd, NB nb) {
     typedef typename Codec<FP>::store_t S;
     S* p = reinterpret_cast<S*>(buf);
-    p[n] = Codec<FP>::enc(f[0]);
+    ddf_st(p + n, Codec<FP>::enc(f[0]));
 #pragma unroll
     for (int i = 1; i < QQ; i += 2) {
-        p[(uint64_t)(i + (int)todd) * N + nb(i)] = Codec<FP>::enc(f[i]);          // t odd ? i+1 : i
-        p[(uint64_t)(i + 1 - (int)todd) * N + n] = Codec<FP>::enc(f[i + 1]);      // t odd ? i : i+1
+        ddf_st(p + ((uint64_t)(i + (int)todd) * N + nb(i)), Codec<FP>::enc(f[i]));          // t odd ? i+1 : i
+        ddf_st(p + ((uint64_t)(i + 1 - (int)todd) * N + n), Codec<FP>::enc(f[i + 1]));      // t odd ? i : i+1
     }
 }
 

@@ -17,6 +17,8 @@
 //     (they do not change register pressure materially); Q, storage codec, MHD and TRT are compile time.
 // No tensor cores: the kernel is HBM-bound (153 B/cell plain, 389 B/cell MHD for D3Q19 FP32).
 #pragma once
+#include <cstdlib>
+
 #include "lattice.cuh"
 
 namespace ion {
@@ -322,6 +324,8 @@ __global__ void __launch_bounds__(SC_BLOCK_MAX) k_initialize(const __grid_consta
 
 inline dim3 cell_grid(const KArgs& a, unsigned& block) {
     unsigned b = ((a.nx + 31u) / 32u) * 32u;
+    static const unsigned cap = getenv("ION_SC_BLOCK") ? (unsigned)atoi(getenv("ION_SC_BLOCK")) : (unsigned)SC_BLOCK_MAX;  // A/B timing only
+    if (b > cap && cap >= 32u && cap <= (unsigned)SC_BLOCK_MAX) b = cap;
     if (b > (unsigned)SC_BLOCK_MAX) b = SC_BLOCK_MAX;
     block = b;
     return dim3((a.nx + b - 1u) / b, a.ny, a.nz);
