@@ -181,6 +181,13 @@ ION_API int ion_exchange_transfer(ion_domain_t* d, ion_domain_t* dp, size_t byte
  * [src_entry, src_entry+entries) of `src` to entry `dst_entry` of `dst` (entries are 4 floats) */
 ION_API int ion_copy_lods(ion_domain_t* dst, uint32_t dst_entry, ion_domain_t* src, uint32_t src_entry, uint32_t entries);
 
+/* Overlap (no reference equivalent: the reference finishes every queue between extract and insert, mod.rs:379).  Between
+ * ion_halo_fork and ion_halo_join the transfer kernels and face exchanges of `dom` are queued on a second stream that starts
+ * after everything queued on the domain so far; ion_halo_join makes the domain's main stream wait for them.  The host layer
+ * uses it to run the fi/fqi/ei halo exchange concurrently with update_e_b_dynamic, which does not touch the DDFs. */
+ION_API int ion_halo_fork(ion_domain_t* dom);
+ION_API int ion_halo_join(ion_domain_t* dom);
+
 /* exchange plan (pure host arithmetic, no GPU needed; used by ion_exchange_transfer's callers, ion_comm_exchange_lods and
  * the host layer, and testable on CPU):
  *   ion_neighbor_domains   ring neighbours of domain d along `axis` (0,1,2): dp = +1 (receives d's transfer_p as its
@@ -206,6 +213,8 @@ ION_API int ion_comm_exchange_lods(ion_comm_t* comm, ion_domain_t* d);
 
 /* instrumentation (no reference equivalent): kernels launched by this library since load, for bench.py */
 ION_API uint64_t ion_kernel_launch_count(void);
+/* FP32 issue-peak probe (FMA/s of the whole device; packed = fma.rn.f32x2): the compute roofline of update_e_b_dynamic */
+ION_API int ion_measure_fma_peak(int device, int packed, double* fma_per_s);
 /* the CUDA stream of a domain (cudaStream_t as void*), so callers can record CUDA events on it */
 ION_API int ion_domain_stream(const ion_domain_t* dom, void** stream);
 

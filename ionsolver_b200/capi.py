@@ -47,6 +47,7 @@ SYMBOLS = [
     "ion_kernel_launch_count", "ion_domain_stream",
     "ion_exchange_transfer", "ion_copy_lods", "ion_comm_unique_id", "ion_comm_create", "ion_comm_destroy",
     "ion_comm_exchange_transfer", "ion_comm_exchange_lods", "ion_neighbor_domains", "ion_lod_exchange_plan",
+    "ion_measure_fma_peak", "ion_halo_fork", "ion_halo_join",
 ]
 # every symbol include/ionsolver_b200_host.h declares
 HOST_SYMBOLS = [
@@ -158,6 +159,9 @@ def load() -> ctypes.CDLL:
     U32P = c.POINTER(c.c_uint32)
     L.ion_neighbor_domains.argtypes = [c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, c.c_uint32, U32P, U32P]
     L.ion_lod_exchange_plan.argtypes = [c.POINTER(IonParams), c.c_uint32, U32P, U32P, U32P]
+    L.ion_halo_fork.argtypes = [D]
+    L.ion_halo_join.argtypes = [D]
+    L.ion_measure_fma_peak.argtypes = [c.c_int, c.c_int, c.POINTER(c.c_double)]
     # ---- host layer (include/ionsolver_b200_host.h) ----
     CFG = c.POINTER(IonLbmConfig)
     H = c.c_void_p
@@ -339,3 +343,10 @@ def lod_exchange_plan(params: IonParams, dc):
     a, b, c_ = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
     check(load().ion_lod_exchange_plan(ctypes.byref(params), dc, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c_)))
     return a.value, b.value, c_.value
+
+
+def measure_fma_peak(device=0, packed=False) -> float:
+    """FP32 FMA/s of the device measured with scalar FFMA (or fma.rn.f32x2): compute roofline for update_e_b_dynamic."""
+    v = ctypes.c_double()
+    check(load().ion_measure_fma_peak(device, int(packed), ctypes.byref(v)))
+    return v.value

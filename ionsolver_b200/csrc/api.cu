@@ -33,6 +33,30 @@ size_t field_source_bytes(uint32_t count);
 cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s);
 cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void* table, cudaStream_t s);
 
+// FP32 issue-peak probe for bench.py's compute roofline (MEASURED_PEAKS.json only carries HBM and BF16 numbers):
+// 16 independent FMA chains per thread, scalar FFMA (PACKED = false) or fma.rn.f32x2 (PACKED = true)
+template <bool PACKED> __global__ void __launch_bounds__(256) k_fma_peak(float* out, float a, float b, int iters) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    const float2 x = make_float2(a, a * 1.0001f), y = make_float2(b, b * 0.9999f);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            if (PACKED) {
+                acc[i] = __ffma2_rn(acc[i], x, y);
+            } else {
+                acc[i].x = fmaf(acc[i].x, x.x, y.x);
+                acc[i].y = fmaf(acc[i].y, x.y, y.y);
+            }
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += acc[i].x + acc[i].y;
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_fill_f32(float* p, uint64_t n, float v) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -76,6 +100,38 @@ extern "C" {
 const char* ion_last_error_string(void) { return g_err; }
 uint32_t ion_abi_version(void) { return ION_ABI_VERSION; }
 uint64_t ion_kernel_launch_count(void) { return g_launches.load(); }
+
+int ion_measure_fma_peak(int device, int packed, double* fma_per_s) {
+    if (!fma_per_s) return fail(ION_ERR_INVALID, "NULL argument");
+    ION_CUDA(cudaSetDevice(device));
+    int sms = 0;
+    ION_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int blocks = sms * 8, threads = 256, iters = 4096;
+    float* out = nullptr;
+    ION_CUDA(cudaMalloc(&out, sizeof(float) * blocks * threads));
+    cudaEvent_t e0, e1;
+    ION_CUDA(cudaEventCreate(&e0));
+    ION_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; rep++) {
+        cudaEventRecord(e0);
+        if (packed) k_fma_peak<true><<<blocks, threads>>>(out, 0.999f, 0.001f, iters);
+        else k_fma_peak<false><<<blocks, threads>>>(out, 0.999f, 0.001f, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep && ms < best) best = ms;
+        g_launches++;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "fma peak probe");
+    *fma_per_s = (double)blocks * threads * iters * 32.0 / (best * 1e-3);
+    return ION_OK;
+}
 
 int ion_device_count(int* count) {
     if (!count) return fail(ION_ERR_INVALID, "count is NULL");
@@ -171,7 +227,10 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
         if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc spare transfer buffers"); }
     }
     e = cudaEventCreateWithFlags(&d->ev, cudaEventDisableTiming);
-    if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaEventCreate"); }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->halo_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaEventCreate / halo stream"); }
     if (mhd) {
         if (deterministic) {
             e = cudaMalloc((void**)&d->lod_u, n * 12);
@@ -231,7 +290,10 @@ int ion_domain_destroy(ion_domain_t* d) {
     if (d->alt_p) cudaFree(d->alt_p);
     if (d->alt_m) cudaFree(d->alt_m);
     if (d->lod_gather) cudaFree(d->lod_gather);
+    if (d->halo_stream) { cudaStreamSynchronize(d->halo_stream); cudaStreamDestroy(d->halo_stream); }
     if (d->ev) cudaEventDestroy(d->ev);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_join) cudaEventDestroy(d->ev_join);
     if (d->stream) cudaStreamDestroy(d->stream);
     delete d;
     return ION_OK;
@@ -405,7 +467,7 @@ static int transfer(ion_domain_t* d, int field, int insert, uint32_t direction, 
     if ((field == ION_TRANSFER_EI || field == ION_TRANSFER_QI) && !(d->params.ext & ION_EXT_MAGNETO_HYDRO))
         return fail(ION_ERR_ABSENT, "transfer kernel needs ext_magneto_hydro (domain.rs:340-367)");
     ION_CUDA(cudaSetDevice(d->device));
-    cudaError_t e = launch_transfer(d->k, (int)d->params.velocity_set, (int)d->params.float_type, field, insert, direction, t, d->stream);
+    cudaError_t e = launch_transfer(d->k, (int)d->params.velocity_set, (int)d->params.float_type, field, insert, direction, t, xfer_stream(d));
     g_launches++;
     if (e != cudaSuccess) return cuda_fail(e, "transfer launch");
     return ION_OK;
@@ -472,9 +534,32 @@ int ion_domain_set_ecr_freq(ion_domain_t* d, float ecrf) {
     return ION_OK;
 }
 
+int ion_halo_fork(ion_domain_t* d) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (d->halo_active) return ION_OK;
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaEventRecord(d->ev_fork, d->stream));
+    ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev_fork, 0));
+    d->halo_active = true;
+    return ION_OK;
+}
+int ion_halo_join(ion_domain_t* d) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (!d->halo_active) return ION_OK;
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaEventRecord(d->ev_join, d->halo_stream));
+    ION_CUDA(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
+    d->halo_active = false;
+    return ION_OK;
+}
+
 int ion_finish(ion_domain_t* d) {
     if (!d) return fail(ION_ERR_INVALID, "NULL domain");
     ION_CUDA(cudaSetDevice(d->device));
+    if (d->halo_active) {
+        int r = ion_halo_join(d);
+        if (r) return r;
+    }
     ION_CUDA(cudaStreamSynchronize(d->stream));
     return ION_OK;
 }

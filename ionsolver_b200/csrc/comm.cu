@@ -62,12 +62,12 @@ int nccl_fail(ncclResult_t r, const char* what) {
     } while (0)
 
 // make `waiter` wait for everything queued on `signaller` so far
-int order_after(ion_domain* waiter, ion_domain* signaller) {
-    if (waiter->stream == signaller->stream) return ION_OK;
+int order_after(ion_domain* waiter, ion_domain* signaller) {  // on the streams the face exchange currently uses
+    if (xfer_stream(waiter) == xfer_stream(signaller)) return ION_OK;
     ION_CUDA(cudaSetDevice(signaller->device));
-    ION_CUDA(cudaEventRecord(signaller->ev, signaller->stream));
+    ION_CUDA(cudaEventRecord(signaller->ev, xfer_stream(signaller)));
     ION_CUDA(cudaSetDevice(waiter->device));
-    ION_CUDA(cudaStreamWaitEvent(waiter->stream, signaller->ev, 0));
+    ION_CUDA(cudaStreamWaitEvent(xfer_stream(waiter), signaller->ev, 0));
     return ION_OK;
 }
 }  // namespace
@@ -102,9 +102,9 @@ int ion_exchange_transfer(ion_domain_t* d, ion_domain_t* dp, size_t bytes) {
     if ((r = order_after(dp, d))) return r;
     if ((r = order_after(d, dp))) return r;
     ION_CUDA(cudaSetDevice(dp->device));
-    ION_CUDA(cudaMemcpyPeerAsync(dp->alt_m, dp->device, d->buf[ION_FIELD_TRANSFER_P], d->device, bytes, dp->stream));
+    ION_CUDA(cudaMemcpyPeerAsync(dp->alt_m, dp->device, d->buf[ION_FIELD_TRANSFER_P], d->device, bytes, xfer_stream(dp)));
     ION_CUDA(cudaSetDevice(d->device));
-    ION_CUDA(cudaMemcpyPeerAsync(d->alt_p, d->device, dp->buf[ION_FIELD_TRANSFER_M], dp->device, bytes, d->stream));
+    ION_CUDA(cudaMemcpyPeerAsync(d->alt_p, d->device, dp->buf[ION_FIELD_TRANSFER_M], dp->device, bytes, xfer_stream(d)));
     // nobody may overwrite a source before the partner's copy has read it
     if ((r = order_after(dp, d))) return r;
     if ((r = order_after(d, dp))) return r;
@@ -212,12 +212,12 @@ int ion_comm_exchange_transfer(ion_comm_t* c, ion_domain_t* d, int rank_p, int r
     // my +face goes to rank_p (their transfer_m), my -face to rank_m (their transfer_p); the mirror images arrive in
     // the spare buffers, which then become current (the device-side equivalent of mod.rs:383)
     ION_NCCL(g_nccl.GroupStart());
-    ION_NCCL(g_nccl.Send(d->buf[ION_FIELD_TRANSFER_P], bytes, ncclUint8, rank_p, c->comm, d->stream));
-    ION_NCCL(g_nccl.Send(d->buf[ION_FIELD_TRANSFER_M], bytes, ncclUint8, rank_m, c->comm, d->stream));
+    ION_NCCL(g_nccl.Send(d->buf[ION_FIELD_TRANSFER_P], bytes, ncclUint8, rank_p, c->comm, xfer_stream(d)));
+    ION_NCCL(g_nccl.Send(d->buf[ION_FIELD_TRANSFER_M], bytes, ncclUint8, rank_m, c->comm, xfer_stream(d)));
     // receive order m, p: with two ranks rank_p == rank_m, and NCCL pairs the k-th send with the k-th receive of a
     // peer -- the partner's first send is ITS +face, which is my new transfer_m
-    ION_NCCL(g_nccl.Recv(d->alt_m, bytes, ncclUint8, rank_m, c->comm, d->stream));
-    ION_NCCL(g_nccl.Recv(d->alt_p, bytes, ncclUint8, rank_p, c->comm, d->stream));
+    ION_NCCL(g_nccl.Recv(d->alt_m, bytes, ncclUint8, rank_m, c->comm, xfer_stream(d)));
+    ION_NCCL(g_nccl.Recv(d->alt_p, bytes, ncclUint8, rank_p, c->comm, xfer_stream(d)));
     ION_NCCL(g_nccl.GroupEnd());
     void* t = d->buf[ION_FIELD_TRANSFER_P];
     d->buf[ION_FIELD_TRANSFER_P] = d->alt_p;

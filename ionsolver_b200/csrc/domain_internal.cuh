@@ -20,6 +20,11 @@ struct ion_domain {
     float* lod_u;         // deterministic mode: per-cell velocity deposits (3N floats)
     float* lod_gather;    // world * n_lod_own * 4 floats, allocated on first ion_comm_exchange_lods
     cudaEvent_t ev;       // reusable ordering event (timing disabled)
+    // halo stream: between ion_halo_fork and ion_halo_join the transfer kernels and the face exchange of this domain run
+    // here, concurrently with whatever is queued on `stream` (update_e_b_dynamic does not touch the DDFs)
+    cudaStream_t halo_stream;
+    cudaEvent_t ev_fork, ev_join;
+    bool halo_active;
     float ecrf;
     bool deterministic;   // ION_EXT_DETERMINISTIC: reference-ordered LOD sums and reference arithmetic in update_e_b_dynamic
 };
@@ -29,6 +34,7 @@ extern std::atomic<uint64_t> g_launches;
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void set_transfer_ptrs(ion_domain* d);  // refresh KArgs after the current/spare transfer buffers were flipped
+inline cudaStream_t xfer_stream(const ion_domain* d) { return d->halo_active ? d->halo_stream : d->stream; }
 }  // namespace ion
 
 #define ION_CUDA(call)                                                  \

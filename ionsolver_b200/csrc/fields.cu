@@ -25,6 +25,24 @@ struct __align__(16) LodSource {
     uint32_t d;  // LOD index d of the reference loop (for the d==ndi self-skip), 0xFFFFFFFF for foreign entries
 };
 
+// One foreign domain's contribution to update_e_b_dynamic (sim.cl:957-983), described for the packed kernel: where its
+// pyramid level sits in QU_lod (entry0) and in the flat source table (flat0), its level, and the centre shift of
+// sim.cl:970-972 (quirks Q8/Q18 included).  `fast` = the level is lod_depth-1 and its block is exactly two own blocks
+// wide in x, so the (cell, source) tile is again Toeplitz-like and the packed tile code applies.
+struct ForeignDesc {
+    uint32_t entry0, flat0, count, level;
+    float sx, sy, sz;
+    uint32_t fast;
+};
+constexpr int MAX_FOREIGN = 32;
+struct ForeignSet {
+    uint32_t n;  // 0: no descriptors, the flat table is walked as a whole
+    ForeignDesc d[MAX_FOREIGN];
+};
+// centres shifted by the uint wrap of quirk Q18 lie ~4.29e9 cells away: their terms are < 1e-16 of the sums they are
+// added to.  The fast path skips them (the deterministic path keeps every term).
+#define ION_FAR_SHIFT 1.0e9f
+
 // lod_coordinates, sim.cl:440-447
 __device__ __forceinline__ void lod_coordinates(const KArgs& a, uint32_t n, uint32_t d, float& cx, float& cy, float& cz) {
     const uint32_t nd = 1u << d;
@@ -348,6 +366,7 @@ __global__ void __launch_bounds__(EBT_BLOCK) k_update_e_b_tiled(const __grid_con
     for (uint32_t f = 0; f < n_foreign; f++) {
         const float4 c = __ldg(reinterpret_cast<const float4*>(foreign + f));
         float4 s = __ldg(reinterpret_cast<const float4*>(foreign + f) + 1);
+        if (!EXACT && (fabsf(c.x) > ION_FAR_SHIFT || fabsf(c.y) > ION_FAR_SHIFT || fabsf(c.z) > ION_FAR_SHIFT)) continue;  // quirk Q18 terms
         s = make_float4(c.w, s.x, s.y, s.z);
         if (!EXACT) { s.y *= s.x; s.z *= s.x; s.w *= s.x; }
         const float ry = fy - c.y, rz = fz - c.z;
@@ -439,7 +458,7 @@ template <bool VOL> __device__ __forceinline__ float4 lds128(const float4* p) {
 
 template <int ND, int NC, int BLOCK, bool VOL>
 __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
-                                                                const uint32_t n_foreign) {
+                                                                const uint32_t n_foreign, const __grid_constant__ ForeignSet fs) {
     static_assert(ND % NC == 0 && NC % 2 == 0, "cells per thread");
     constexpr int PARTS = ND / NC;
     extern __shared__ float4 s_pair[];  // slot t -> {q_t, q_t', wx_t, wx_t'}, {wy_t, wy_t', wz_t, wz_t'}; t' = next source of the row, cyclic
@@ -553,18 +572,70 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
     }
 
     // ---- foreign-domain LODs (sim.cl:957-983) ----
-    for (uint32_t f = 0; f < n_foreign; f++) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(foreign + f));
-        float4 s = __ldg(reinterpret_cast<const float4*>(foreign + f) + 1);
-        s = make_float4(c.w, s.x * c.w, s.y * c.w, s.z * c.w);
-        const float ry = fy - c.y, rz = fz - c.z;
+    // generic: one source against the NC cells, r/|r|^3 evaluated per (cell, source) with packed FP32
+    auto foreign_generic = [&](uint32_t f0, uint32_t f1) {
+        for (uint32_t f = f0; f < f1; f++) {
+            const float4 c = __ldg(reinterpret_cast<const float4*>(foreign + f));
+            if (fabsf(c.x) > ION_FAR_SHIFT || fabsf(c.y) > ION_FAR_SHIFT || fabsf(c.z) > ION_FAR_SHIFT) continue;  // quirk Q18 terms
+            float4 s = __ldg(reinterpret_cast<const float4*>(foreign + f) + 1);
+            s = make_float4(c.w, s.x * c.w, s.y * c.w, s.z * c.w);
+            const float ry = fy - c.y, rz = fz - c.z;
+            const float ryz2 = fmaf(ry, ry, rz * rz);
 #pragma unroll
-        for (int j = 0; j < NC / 2; j++) {
-            float p0x, p0y, p0z, p1x, p1y, p1z;
-            pre_field<false>((float)((kbase + (uint32_t)(2 * j)) * dsx + ox) - c.x, ry, rz, p0x, p0y, p0z);
-            pre_field<false>((float)((kbase + (uint32_t)(2 * j + 1)) * dsx + ox) - c.x, ry, rz, p1x, p1y, p1z);
-            fma_pair(e2[j], b2[j], make_float4(s.x, s.x, s.y, s.y), make_float4(s.z, s.z, s.w, s.w), make_float2(p0x, p1x), make_float2(p0y, p1y),
-                     make_float2(p0z, p1z));
+            for (int j = 0; j < NC / 2; j++) {
+                const float2 rx = make_float2((float)((kbase + (uint32_t)(2 * j)) * dsx + ox) - c.x, (float)((kbase + (uint32_t)(2 * j + 1)) * dsx + ox) - c.x);
+                const float2 r2 = __ffma2_rn(rx, rx, make_float2(ryz2, ryz2));
+                const float2 ri = make_float2(r2.x > 0.0f ? rsqrtf(r2.x) : 0.0f, r2.y > 0.0f ? rsqrtf(r2.y) : 0.0f);
+                const float2 ri3 = __fmul2_rn(__fmul2_rn(ri, ri), ri);
+                fma_pair(e2[j], b2[j], make_float4(s.x, s.x, s.y, s.y), make_float4(s.z, s.z, s.w, s.w), __fmul2_rn(rx, ri3),
+                         __fmul2_rn(make_float2(ry, ry), ri3), __fmul2_rn(make_float2(rz, rz), ri3));
+            }
+        }
+    };
+    if (fs.n == 0u) {
+        foreign_generic(0u, n_foreign);
+    } else {
+        for (uint32_t fi = 0; fi < fs.n; fi++) {
+            const ForeignDesc& fd = fs.d[fi];
+            if (fabsf(fd.sx) > ION_FAR_SHIFT || fabsf(fd.sy) > ION_FAR_SHIFT || fabsf(fd.sz) > ION_FAR_SHIFT) continue;  // quirk Q18 domains
+            if (!fd.fast) {
+                foreign_generic(fd.flat0, fd.flat0 + fd.count);
+                continue;
+            }
+            // Level lod_depth-1 of a neighbour: ND/2 sources per row, each two own blocks wide.  Cells (2j, 2j+1) against
+            // source cx have r_x = (2m-1)*dsx + ox + sx and 2m*dsx + ox + sx with m = j - cx: 2*(NC/2 + ND/2) - 1 packed
+            // r/|r|^3 pairs serve the NC*ND/2 pairs of a row; the source enters as the broadcast operand.
+            constexpr int NF = ND / 2;
+            const float bsy = (float)(a.ny / NF), bsz = (float)(a.nz / NF);
+            const float rxb = (float)(kbase * dsx + ox) + fd.sx;  // r_x of cell kl = 0 against a source whose centre is at 0
+            const float4* __restrict__ lod = reinterpret_cast<const float4*>(a.QU_lod) + fd.entry0;
+            for (uint32_t row = 0; row < (uint32_t)(NF * NF); row++) {
+                const uint32_t cy = row % NF, cz = row / NF;
+                const float ry = fy - (((float)cy * bsy + 0.5f * bsy) - fd.sy);
+                const float rz = fz - (((float)cz * bsz + 0.5f * bsz) - fd.sz);
+                const float ryz2 = fmaf(ry, ry, rz * rz);
+                float4 src[NF];
+#pragma unroll
+                for (int cx = 0; cx < NF; cx++) {
+                    const float4 v = __ldg(lod + row * NF + cx);
+                    src[cx] = make_float4(v.x, v.y * v.x, v.z * v.x, v.w * v.x);
+                }
+#pragma unroll
+                for (int m = -(NF - 1); m < NC / 2; m++) {
+                    const float2 rx = make_float2((float)(2 * m - 1) * dsxf + rxb, (float)(2 * m) * dsxf + rxb);
+                    const float2 r2 = __ffma2_rn(rx, rx, make_float2(ryz2, ryz2));
+                    const float2 ri = make_float2(r2.x > 0.0f ? rsqrtf(r2.x) : 0.0f, r2.y > 0.0f ? rsqrtf(r2.y) : 0.0f);
+                    const float2 ri3 = __fmul2_rn(__fmul2_rn(ri, ri), ri);
+                    const float2 px = __fmul2_rn(rx, ri3), py = __fmul2_rn(make_float2(ry, ry), ri3), pz = __fmul2_rn(make_float2(rz, rz), ri3);
+#pragma unroll
+                    for (int j = 0; j < NC / 2; j++) {
+                        const int cx = j - m;
+                        if (cx < 0 || cx >= NF) continue;
+                        const float4 sv = src[cx];
+                        fma_pair(e2[j], b2[j], make_float4(sv.x, sv.x, sv.y, sv.y), make_float4(sv.z, sv.z, sv.w, sv.w), px, py, pz);
+                    }
+                }
+            }
         }
     }
 
@@ -651,6 +722,35 @@ __global__ void k_lod_gather(float* __restrict__ lods, uint32_t depth) {
 }
 
 // ---- launchers used by api.cu ----
+// descriptors of the foreign domains in the order k_build_sources lays them out (ascending index, self skipped)
+static void describe_foreign(const KArgs& a, uint32_t nd, ForeignSet& fs) {
+    fs.n = 0;
+    const uint32_t dxy = a.dx * a.dy, dn = dxy * a.dz;
+    if (dn <= 1u || dn - 1u > (uint32_t)MAX_FOREIGN) return;  // single domain, or too many: the kernel walks the flat table
+    const int cdx = (int)((a.di % dxy) % a.dx), cdy = (int)((a.di % dxy) / a.dx), cdz = (int)(a.di / dxy);
+    uint32_t entry = a.n_lod_own, flat = 0;
+    for (uint32_t d = 0; d < dn; d++) {
+        if (d == a.di) continue;
+        const int ddx = cdx - (int)((d % dxy) % a.dx), ddy = cdy - (int)((d % dxy) / a.dx), ddz = cdz - (int)(d / dxy);
+        int dist = abs(ddx);
+        if (abs(ddy) > dist) dist = abs(ddy);
+        if (abs(ddz) > dist) dist = abs(ddz);
+        const uint32_t level = (int)a.lod_depth - dist > 0 ? (uint32_t)((int)a.lod_depth - dist) : 0u;
+        const uint32_t ndf = 1u << level, cnt = ndf * ndf * ndf;
+        ForeignDesc& f = fs.d[fs.n++];
+        f.entry0 = entry;
+        f.flat0 = flat;
+        f.count = cnt;
+        f.level = level;
+        f.sx = (float)((uint32_t)ddx * a.nx);  // sim.cl:970-972 incl. the uint wrap of negative differences (quirk Q18)
+        f.sy = (float)((uint32_t)ddy * a.ny);
+        f.sz = (float)((uint32_t)ddz * a.nz);
+        f.fast = (level + 1u == a.lod_depth && 2u * ndf == nd && a.nx / ndf == 2u * (a.nx / nd) && a.ny >= ndf && a.nz >= ndf) ? 1u : 0u;
+        entry += cnt;
+        flat += cnt;
+    }
+}
+
 template <int ND, int NC, int BLOCK, bool VOL>
 static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s) {
     const size_t smem = (size_t)own * 2 * sizeof(float4);
@@ -658,9 +758,11 @@ static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t ow
         cudaError_t e = cudaFuncSetAttribute(k_update_e_b_pair<ND, NC, BLOCK, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * fine_bytes(ND)));
         if (e != cudaSuccess) return e;
     }
+    ForeignSet fs;
+    describe_foreign(a, ND, fs);
     const uint32_t threads_per_plane = (a.nx / ND) * (ND / NC) * a.ny;
     const dim3 grid((threads_per_plane + BLOCK - 1) / BLOCK, a.nz);
-    k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own);
+    k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own, fs);
     return cudaGetLastError();
 }
 

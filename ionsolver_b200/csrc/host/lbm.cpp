@@ -346,23 +346,38 @@ void Lbm::run(uint64_t steps) {  // mod.rs:235-245
 }
 
 void Lbm::do_time_step() {  // mod.rs:250-272
-    if (config.ext_magneto_hydro) clear_qu_lod();
+    const bool mhd = config.ext_magneto_hydro;
+    if (mhd) clear_qu_lod();
     stream_collide();
     if (config.graphics_config.graphics_active) communicate_rho_u_flags();
-    communicate_fi();
-    if (config.ext_magneto_hydro) {
-        if (get_d_n() > 1) build_lods_part_2();
+    if (mhd && get_d_n() > 1 && overlap_halo) {
+        // Same operations as the reference sequence below, re-ordered so that they overlap: the LOD pyramids are gathered
+        // and exchanged first (update_e_b_dynamic needs only them), then the fi / fqi / ei halo exchange runs on the
+        // domains' halo streams while update_e_b_dynamic -- which never touches a DDF -- runs on the main streams.
+        build_lods_part_2();
+        communicate_qu_lods();
+        for (auto& d : domains) check(ion_halo_fork(d.dev));
+        communicate_fi();
         communicate_fqi();
         communicate_ei();
-        communicate_qu_lods();
         update_e_b_dynamic();
+        for (auto& d : domains) check(ion_halo_join(d.dev));
+    } else {
+        communicate_fi();
+        if (mhd) {
+            if (get_d_n() > 1) build_lods_part_2();
+            communicate_fqi();
+            communicate_ei();
+            communicate_qu_lods();
+            update_e_b_dynamic();
+        }
     }
     // mod.rs:267-270 blocks here (`finish_queues`) in the single-domain and MHD cases.  On an in-order CUDA stream
     // the next step is ordered behind this one anyway, so the host does not stall; callers that need completion
     // call finish_queues() (run() does not need it, reads through ion_buffer_read synchronise by themselves).
     // Exception: several domains in ONE process exchange LOD pyramids by cross-stream copies, and the next step's
     // clear_qu_lod of a fast domain must not overtake a slow neighbour's copy -- keep the reference's barrier there.
-    if (config.ext_magneto_hydro && world == 1 && get_d_n() > 1) finish_queues();
+    if (mhd && world == 1 && get_d_n() > 1) finish_queues();
     increment_timestep(1);
 }
 

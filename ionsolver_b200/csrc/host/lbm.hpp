@@ -13,6 +13,7 @@
 #pragma once
 #include <cstdint>
 #include <stdexcept>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -179,6 +180,9 @@ struct Lbm {
     LbmConfig config;
     std::vector<Mesh> meshes;
     bool initialized = false;
+    // run the fi/fqi/ei halo exchange concurrently with update_e_b_dynamic (MHD, more than one domain); ION_NO_OVERLAP=1
+    // restores the reference's strictly sequential order for A/B timing
+    bool overlap_halo = !(getenv("ION_NO_OVERLAP") && atoi(getenv("ION_NO_OVERLAP")) != 0);
     // one process per GPU: rank owns domain `rank`; comm carries the halo exchange (NCCL over NVLink)
     ion_comm_t* comm = nullptr;
     int rank = 0, world = 1;

@@ -24,6 +24,16 @@
 namespace ion {
 
 constexpr int SC_BLOCK_MAX = 256;
+// stream_collide launch shape.  Measured at 256^3 D3Q19 FP32 MHD (profiles/r1_stream_collide_ab.md): blocks of 64 threads
+// reach 5.12 TB/s, 128 -> 5.07, 256 -> 4.76 (8 / 4 / 2 resident blocks per SM at 128 registers: finer blocks drain and refill
+// the SM more evenly, so fewer bytes-in-flight bubbles at block boundaries).  ION_SC_MINB is a build-time experiment switch
+// (register cap = 65536 / (ION_SC_BLOCK * ION_SC_MINB)).
+#ifndef ION_SC_BLOCK
+#define ION_SC_BLOCK 64
+#endif
+#ifndef ION_SC_MINB
+#define ION_SC_MINB 8
+#endif
 
 struct LodDeposit {
     uint32_t ind;  // float index of the LOD entry (already *4), 0xFFFFFFFF = nothing to deposit
@@ -59,18 +69,34 @@ __device__ __forceinline__ void lod_deposit_warp(float* __restrict__ QU_lod, Lod
 }
 
 template <int VS, int FP, bool MHD, bool TRT>
-__global__ void __launch_bounds__(SC_BLOCK_MAX)
+__global__ void __launch_bounds__(ION_SC_BLOCK, ION_SC_MINB)
 k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float fx, const float fy, const float fz) {
     constexpr int QQ = VSet<VS>::Q;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
-    bool active = x < a.nx && !is_halo(a, x, y, z);  // sim.cl:485
-    const Cell c = make_cell(a, active ? x : 0u, y, z);
+    const bool inside = x < a.nx && !is_halo(a, x, y, z);  // sim.cl:485
+    const Cell c = make_cell(a, inside ? x : 0u, y, z);
     const uint32_t n = c.n;
-    uint8_t flagsn = 0;
-    if (active) {
-        flagsn = a.flags[n];
-        active = (flagsn & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:487-488 (quirk Q1: only exact TYPE_S is solid)
+    const uint64_t N = a.N;
+    const uint64_t todd = t & 1ull;
+    auto nb = [&](int i) { return neighbor<VS>(c, i); };
+
+    // ---- every load of the cell is issued BEFORE the flag is known (sim.cl:487 returns first): the flag byte would
+    // otherwise cost one full HBM round trip during which the warp has nothing in flight.  A solid cell's DDFs are read and
+    // dropped (a few % extra reads in scenes with solids, none in the fluid bulk); results are unchanged. ----
+    const uint8_t flagsn = inside ? a.flags[n] : (uint8_t)ION_TYPE_S;
+    float fhn[QQ];
+    ep_load<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 2, sim.cl:494
+    float ehn[MHD ? QQ : 1];
+    float qhn[7];
+    float Bx = 0.f, By = 0.f, Bz = 0.f, Ex = 0.f, Ey = 0.f, Ez = 0.f;
+    if (MHD) {
+        Bx = a.B_dyn[n]; By = a.B_dyn[N + n]; Bz = a.B_dyn[2ull * N + n];  // sim.cl:532-533
+        Ex = a.E_dyn[n]; Ey = a.E_dyn[N + n]; Ez = a.E_dyn[2ull * N + n];
+        ep_load<FP, QQ>(ehn, a.ei, N, n, todd, nb);                         // sim.cl:538
+        ep_load<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
     }
+    const bool active = (flagsn & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:487-488 (quirk Q1: only exact TYPE_S is solid)
+
     LodDeposit dep;
     dep.ind = 0xFFFFFFFFu;
     dep.q = dep.ux = dep.uy = dep.uz = 0.0f;
@@ -78,26 +104,9 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
 
     if (active) {
         const uint8_t bo = flagsn & ION_TYPE_BO;
-        const uint64_t N = a.N;
-        const uint64_t todd = t & 1ull;
         const bool eqb = (a.ext & ION_EXT_EQUILIBRIUM_BOUNDARIES) != 0u;
         const bool vf = (a.ext & ION_EXT_VOLUME_FORCE) != 0u;
         const bool is_e = eqb && bo == ION_TYPE_E;
-        auto nb = [&](int i) { return neighbor<VS>(c, i); };
-
-        float fhn[QQ];
-        ep_load<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 2, sim.cl:494
-
-        // ---- issue the MHD loads early so that they overlap with the gas moments ----
-        float ehn[MHD ? QQ : 1];
-        float qhn[7];
-        float Bx = 0.f, By = 0.f, Bz = 0.f, Ex = 0.f, Ey = 0.f, Ez = 0.f;
-        if (MHD) {
-            Bx = a.B_dyn[n]; By = a.B_dyn[N + n]; Bz = a.B_dyn[2ull * N + n];  // sim.cl:532-533
-            Ex = a.E_dyn[n]; Ey = a.E_dyn[N + n]; Ez = a.E_dyn[2ull * N + n];
-            ep_load<FP, QQ>(ehn, a.ei, N, n, todd, nb);                         // sim.cl:538
-            ep_load<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
-        }
 
         float rhon, uxn, uyn, uzn;
         if (is_e) {  // sim.cl:503-507
@@ -322,13 +331,16 @@ __global__ void __launch_bounds__(SC_BLOCK_MAX) k_initialize(const __grid_consta
     }
 }
 
-inline dim3 cell_grid(const KArgs& a, unsigned& block) {
+inline dim3 cell_grid(const KArgs& a, unsigned& block, unsigned cap = SC_BLOCK_MAX) {
     unsigned b = ((a.nx + 31u) / 32u) * 32u;
-    static const unsigned cap = getenv("ION_SC_BLOCK") ? (unsigned)atoi(getenv("ION_SC_BLOCK")) : (unsigned)SC_BLOCK_MAX;  // A/B timing only
-    if (b > cap && cap >= 32u && cap <= (unsigned)SC_BLOCK_MAX) b = cap;
-    if (b > (unsigned)SC_BLOCK_MAX) b = SC_BLOCK_MAX;
+    if (b > cap) b = cap;
     block = b;
     return dim3((a.nx + b - 1u) / b, a.ny, a.nz);
+}
+inline dim3 sc_grid(const KArgs& a, unsigned& block) {  // stream_collide: ION_SC_BLOCK threads, env ION_SC_BLOCK may lower it (A/B timing)
+    static const unsigned env = getenv("ION_SC_BLOCK") ? (unsigned)atoi(getenv("ION_SC_BLOCK")) : 0u;
+    const unsigned cap = (env >= 32u && env <= (unsigned)ION_SC_BLOCK) ? env : (unsigned)ION_SC_BLOCK;
+    return cell_grid(a, block, cap);
 }
 
 // per-velocity-set launchers (one translation unit each, see sc_d*.cu)
@@ -350,7 +362,7 @@ template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool 
                                               float fy, float fz, cudaStream_t s) {                                  \
         constexpr int VS = VSV;                                                                                      \
         unsigned block;                                                                                              \
-        const dim3 grid = cell_grid(a, block);                                                                       \
+        const dim3 grid = sc_grid(a, block);                                                                         \
         ION_SC_CASE(ION_FP32, false, false)                                                                          \
         ION_SC_CASE(ION_FP32, false, true)                                                                           \
         ION_SC_CASE(ION_FP16S, false, false)                                                                         \

@@ -85,6 +85,14 @@ def multi_domain_mhd_cases():
                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True))),
         ("mhd_z4_d3q19_fp16s_lod1", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=8, n_y=8, n_z=24, d_z=4, nu=0.05,
                                           ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=1), 8.0)),
+        # depth 3 / 4: the tiled and packed update_e_b_dynamic kernels with foreign-domain pyramids (level depth-1 of the
+        # neighbour slab: 64 / 512 sources); local size incl. halos 16^3
+        ("mhd_z2_d3q19_fp32_lod3", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
+                                         ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=3), 16.0)),
+        ("mhd_z2_d3q19_fp32_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
+                                         ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True), 16.0)),
+        ("mhd_z3_d3q19_fp32_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=16, n_z=42, d_z=3, nu=0.05,
+                                         ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
     ]
 
 

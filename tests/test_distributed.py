@@ -76,7 +76,7 @@ def test_exchange_plan_against_reference_arithmetic():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["z2_d3q19_fp32", "mhd_z2_d3q19_fp32_lod2"])
+@pytest.mark.parametrize("case", ["z2_d3q19_fp32", "mhd_z2_d3q19_fp32_lod2", "mhd_z2_d3q19_fp32_lod4"])
 def test_two_ranks_nccl(case, gpu_lib):
     from ionsolver_b200 import capi
     if capi.device_count() < 2:
