@@ -14,7 +14,7 @@
 namespace ion {
 // launchers implemented in the kernel translation units
 template <int VS>
-cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx, float fy, float fz,
+cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, bool ecr, uint64_t t, float fx, float fy, float fz,
                                      cudaStream_t s);
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
@@ -168,7 +168,7 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
         if (p->n_lod_own == 0 || p->n_lod < p->n_lod_own) return fail(ION_ERR_INVALID, "bad LOD counts");
         if ((uint64_t)(p->nx + 2u) * (p->ny + 2u) * (p->nz + 2u) > 3ull * n) return fail(ION_ERR_UNSUPPORTED, "padded psi grid does not fit the E_dyn scratch (sim_kernels.cl:1234, domain.rs:280)");
     }
-    if (ecr) return fail(ION_ERR_UNSUPPORTED, "SUBGRID_ECR is not built yet (SURVEY section 8 row f3)");
+    if (ecr && !mhd) return fail(ION_ERR_UNSUPPORTED, "SUBGRID_ECR needs MAGNETO_HYDRO (its code sits inside the MHD block, sim_kernels.cl:556)");
     const bool deterministic = mhd && (p->ext & ION_EXT_DETERMINISTIC);
     if (deterministic && p->lod_depth > 0u) {
         const uint32_t nd = 1u << p->lod_depth;
@@ -205,6 +205,11 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
         B[ION_FIELD_EI] = n * q * s;
         B[ION_FIELD_Q] = n * 4;
         B[ION_FIELD_QU_LOD] = (size_t)p->n_lod * 16;
+    }
+    if (ecr) {  // domain.rs:200-211
+        B[ION_FIELD_E_VAR] = n * 12;
+        B[ION_FIELD_ETI] = n * 7 * s;
+        B[ION_FIELD_ET] = n * 4;
     }
     size_t a_max = 0;  // domain.rs:311-318
     if (p->dx > 1) a_max = a_max > (size_t)p->ny * p->nz ? a_max : (size_t)p->ny * p->nz;
@@ -399,7 +404,8 @@ int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, 
     cudaError_t e;
     const bool mhd = d->params.ext & ION_EXT_MAGNETO_HYDRO;
     const bool trt = d->params.relaxation_time == ION_TRT;
-    ION_VS_DISPATCH(launch_stream_collide_vs, d->k, (int)d->params.float_type, mhd, trt, t, fx, fy, fz, d->stream)
+    const bool ecr = d->params.ext & ION_EXT_SUBGRID_ECR;
+    ION_VS_DISPATCH(launch_stream_collide_vs, d->k, (int)d->params.float_type, mhd, trt, ecr, t, fx, fy, fz, d->stream)
     g_launches++;
     if (e != cudaSuccess) return cuda_fail(e, "stream_collide launch");
     if (mhd && d->deterministic && d->params.lod_depth > 0u) {  // ordered LOD sums instead of the in-kernel float atomics

@@ -68,8 +68,23 @@ __device__ __forceinline__ void lod_deposit_warp(float* __restrict__ QU_lod, Lod
     }
 }
 
-template <int VS, int FP, bool MHD, bool TRT>
-__global__ void __launch_bounds__(ION_SC_BLOCK, ION_SC_MINB)
+// Resident blocks per SM the register allocation has to allow.  The MHD kernel keeps 2Q+7+6 loaded values live (128
+// registers, 8 blocks of 64 threads; capping it lower spills and is slower).  The plain kernel has only Q loads per thread in
+// flight, so it needs more warps to cover the HBM latency: measured at 256^3 FP32 (profiles/r1_stream_collide_ab.md) D3Q19
+// reaches 4.87 TB/s at <= 64 registers (16 blocks) against 4.32 TB/s at 128; D3Q27 is best at <= 112 registers (9 blocks).
+#ifndef ION_SC_MINB_PLAIN
+#define ION_SC_MINB_PLAIN 16
+#endif
+template <int VS, bool MHD> struct ScMinBlocks { static constexpr int value = MHD ? ION_SC_MINB : (VSet<VS>::Q > 19 ? 9 : ION_SC_MINB_PLAIN); };
+
+// SUBGRID_ECR helpers, sim.cl:449-461
+__device__ __forceinline__ float mag_v(const float* __restrict__ V, uint64_t N, uint32_t n) {
+    return sqrtf(sq(V[n]) + sq(V[N + n]) + sq(V[2ull * N + n]));
+}
+__device__ __forceinline__ float length3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }  // OpenCL length()
+
+template <int VS, int FP, bool MHD, bool TRT, bool ECR>
+__global__ void __launch_bounds__(ION_SC_BLOCK, ScMinBlocks<VS, MHD>::value)
 k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float fx, const float fy, const float fz) {
     constexpr int QQ = VSet<VS>::Q;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
@@ -94,6 +109,12 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
         Ex = a.E_dyn[n]; Ey = a.E_dyn[N + n]; Ez = a.E_dyn[2ull * N + n];
         ep_load<FP, QQ>(ehn, a.ei, N, n, todd, nb);                         // sim.cl:538
         ep_load<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
+    }
+    float ethn[ECR ? 7 : 1];
+    float Evx = 0.f, Evy = 0.f, Evz = 0.f;
+    if (ECR) {
+        ep_load<FP, 7>(ethn, a.eti, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:566
+        Evx = a.E_var[n]; Evy = a.E_var[N + n]; Evz = a.E_var[2ull * N + n];                // sim.cl:579
     }
     const bool active = (flagsn & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:487-488 (quirk Q1: only exact TYPE_S is solid)
 
@@ -137,6 +158,44 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
 #pragma unroll
             for (int i = 0; i < 7; i++) rhon_q += qhn[i];
             rhon_q += 1.0f;
+            if (ECR) {  // sim.cl:556-629.  rel_absorbtion (sim.cl:582-585, the only double-precision expression) is computed
+                        // and printed by the reference but never used, so it is not evaluated here.
+                float Etn = 0.0f;  // electron temperature 1
+#pragma unroll
+                for (int i = 0; i < 7; i++) Etn += ethn[i];
+                Etn += 1.0f;
+                // ECR heating: field component perpendicular to B
+                const float lb = length3(Bx, By, Bz);
+                const float sc = (Evx * Bx + Evy * By + Evz * Bz) / sq(lb);
+                const float Env_mag = length3(Evx - sc * Bx, Evy - sc * By, Evz - sc * Bz);
+                Etn += a.keabs / a.kkbme * (rhon_e + 0.00001f) / a.kkge * sq(Env_mag);
+                // drift of gyrating electrons along grad|B| (central differences with the reference's `a - b / 2.0f`)
+                float gx = 0.0f, gy = 0.0f, gz = 0.0f;
+                if (!(x == 0u || x == a.nx - 1u || y == 0u || y == a.ny - 1u || z == 0u || z == a.nz - 1u)) {
+                    const uint32_t nxy = a.nx * a.ny;
+                    gx = mag_v(a.B_dyn, N, n + 1u) - mag_v(a.B_dyn, N, n - 1u) / 2.0f;
+                    gy = mag_v(a.B_dyn, N, n + a.nx) - mag_v(a.B_dyn, N, n - a.nx) / 2.0f;
+                    gz = mag_v(a.B_dyn, N, n + nxy) - mag_v(a.B_dyn, N, n - nxy) / 2.0f;
+                }
+                const float ke_t = a.kkbme * Etn;
+                const float dux = (ke_t * gx) / lb, duy = (ke_t * gy) / lb, duz = (ke_t * gz) / lb;
+                uxn_e += dux;
+                uyn_e += duy;
+                uzn_e += duz;
+                Etn -= length3(dux, duy, duz) / a.kkbme;
+                // electron temperature 2
+                float eteq[7];
+                a_eq(Etn, uxn_e, uyn_e, uzn_e, eteq);
+                if (a.ext & ION_EXT_UPDATE_FIELDS) a.Et[n] = Etn;
+                const float wq = a.wq;
+#pragma unroll
+                for (int i = 0; i < 7; i++) ethn[i] = fmaf(1.0f - wq, ethn[i], wq * eteq[i]);
+                ep_store<FP, 7>(ethn, a.eti, N, n, todd, [&](int i) { return neighbor7(c, i); });
+                // ionization
+                const float delta_q_rho = 0.0001f * Etn;
+                rhon_e += delta_q_rho;
+                rhon_q += delta_q_rho;
+            }
             // gas charge advection 2, sim.cl:633-637
             a.Q[n] = rhon_q - rhon_e;
             {
@@ -345,37 +404,43 @@ inline dim3 sc_grid(const KArgs& a, unsigned& block) {  // stream_collide: ION_S
 
 // per-velocity-set launchers (one translation unit each, see sc_d*.cu)
 template <int VS>
-cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx, float fy, float fz,
+cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt, bool ecr, uint64_t t, float fx, float fy, float fz,
                                      cudaStream_t s);
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
 
-#define ION_SC_CASE(FPV, MHDV, TRTV)                                                                   \
-    if (fp == FPV && mhd == MHDV && trt == TRTV) {                                                     \
-        k_stream_collide<VS, FPV, MHDV, TRTV><<<grid, block, 0, s>>>(a, t, fx, fy, fz);                \
+#define ION_SC_CASE(FPV, MHDV, TRTV, ECRV)                                                             \
+    if (fp == FPV && mhd == MHDV && trt == TRTV && ecr == ECRV) {                                      \
+        k_stream_collide<VS, FPV, MHDV, TRTV, ECRV><<<grid, block, 0, s>>>(a, t, fx, fy, fz);          \
         return cudaGetLastError();                                                                     \
     }
 
 #define ION_DEFINE_VS_LAUNCHERS(VSV, ALLOW_MHD)                                                                      \
     template <>                                                                                                      \
-    cudaError_t launch_stream_collide_vs<VSV>(const KArgs& a, int fp, bool mhd, bool trt, uint64_t t, float fx,      \
-                                              float fy, float fz, cudaStream_t s) {                                  \
+    cudaError_t launch_stream_collide_vs<VSV>(const KArgs& a, int fp, bool mhd, bool trt, bool ecr, uint64_t t,      \
+                                              float fx, float fy, float fz, cudaStream_t s) {                        \
         constexpr int VS = VSV;                                                                                      \
         unsigned block;                                                                                              \
         const dim3 grid = sc_grid(a, block);                                                                         \
-        ION_SC_CASE(ION_FP32, false, false)                                                                          \
-        ION_SC_CASE(ION_FP32, false, true)                                                                           \
-        ION_SC_CASE(ION_FP16S, false, false)                                                                         \
-        ION_SC_CASE(ION_FP16S, false, true)                                                                          \
-        ION_SC_CASE(ION_FP16C, false, false)                                                                         \
-        ION_SC_CASE(ION_FP16C, false, true)                                                                          \
+        ION_SC_CASE(ION_FP32, false, false, false)                                                                   \
+        ION_SC_CASE(ION_FP32, false, true, false)                                                                    \
+        ION_SC_CASE(ION_FP16S, false, false, false)                                                                  \
+        ION_SC_CASE(ION_FP16S, false, true, false)                                                                   \
+        ION_SC_CASE(ION_FP16C, false, false, false)                                                                  \
+        ION_SC_CASE(ION_FP16C, false, true, false)                                                                   \
         if (ALLOW_MHD) {                                                                                             \
-            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, false)                                                            \
-            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, true)                                                             \
-            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, false)                                                           \
-            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, true)                                                            \
-            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, false)                                                           \
-            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, true)                                                            \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, false, false)                                                     \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, true, false)                                                      \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, false, false)                                                    \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, true, false)                                                     \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, false, false)                                                    \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, true, false)                                                     \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, false, (bool)ALLOW_MHD)                                           \
+            ION_SC_CASE(ION_FP32, (bool)ALLOW_MHD, true, (bool)ALLOW_MHD)                                            \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, false, (bool)ALLOW_MHD)                                          \
+            ION_SC_CASE(ION_FP16S, (bool)ALLOW_MHD, true, (bool)ALLOW_MHD)                                           \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, false, (bool)ALLOW_MHD)                                          \
+            ION_SC_CASE(ION_FP16C, (bool)ALLOW_MHD, true, (bool)ALLOW_MHD)                                           \
         }                                                                                                            \
         return cudaErrorInvalidValue;                                                                                \
     }                                                                                                                \

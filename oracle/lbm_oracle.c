@@ -12,7 +12,7 @@
  * kernel source compiled for the host (oracle/_ref, built by oracle/build_ref.py from /root/reference), and
  * tests/golden/ holds outputs of that reference build for machines where /root/reference is absent.
  *
- * Not restated: SUBGRID_ECR (sim.cl:449-462,556-629).
+ * SUBGRID_ECR (sim.cl:449-462,556-629,827-831) is restated too (stream_collide_cell, ora_initialize).
  */
 #include <math.h>
 #include <stdint.h>
@@ -34,6 +34,9 @@ typedef struct OraParams {
     float ke, kmu, kmu0, kkge, wq;
     uint32_t lod_depth, n_lod, n_lod_own;
     int32_t threads;              /* OpenMP threads, 0 = default */
+    uint32_t subgrid_ecr;         /* SUBGRID_ECR (domain.rs:850-854) */
+    float kme, kkbme, keabs;      /* DEF_KME, DEF_KKBME, DEF_KEABS */
+    float ecrf;                   /* kernel argument "ecrf" (domain.rs:292-296) */
 } OraParams;
 
 typedef struct OraBuffers {
@@ -41,6 +44,7 @@ typedef struct OraBuffers {
     float* E_stat; float* B_stat; float* E_dyn; float* B_dyn;
     void* fqi; void* ei; float* Q; float* QU_lod;
     uint8_t* transfer_p; uint8_t* transfer_m;
+    float* E_var; void* eti; float* Et;  /* SUBGRID_ECR (domain.rs:200-211) */
 } OraBuffers;
 
 #define TYPE_S 0x01
@@ -295,6 +299,23 @@ static void set_threads(const OraParams* p) {
 }
 
 /* =============================== stream_collide, sim.cl:465-758 =============================== */
+/* SUBGRID_ECR helpers, sim.cl:449-461 */
+static inline float length3(const float* v) { return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }  /* OpenCL length() */
+static float mag_v(const Ctx* k, uint32_t n, const float* V) {
+    return sqrtf(sq(V[n]) + sq(V[k->N + (uint64_t)n]) + sq(V[2ul * k->N + (uint64_t)n]));
+}
+static void grad_mag_v(const Ctx* k, uint32_t n, const float* V, float* g) {
+    uint32_t x, y, z;
+    coordinates(k, n, &x, &y, &z);
+    const OraParams* p = k->p;
+    if (x == 0 || x == p->nx - 1 || y == 0 || y == p->ny - 1 || z == 0 || z == p->nz - 1) { g[0] = g[1] = g[2] = 0.0f; return; }
+    const uint32_t nx = p->nx, nxy = p->nx * p->ny;
+    /* `a - b / 2.0f`: the division binds to the second term only (sim.cl:457-459), kept */
+    g[0] = mag_v(k, n + 1u, V) - mag_v(k, n - 1u, V) / 2.0f;
+    g[1] = mag_v(k, n + nx, V) - mag_v(k, n - nx, V) / 2.0f;
+    g[2] = mag_v(k, n + nxy, V) - mag_v(k, n - nxy, V) / 2.0f;
+}
+
 static void stream_collide_cell(const Ctx* k, const OraBuffers* b, uint32_t n, uint64_t t, float fx, float fy, float fz) {
     const OraParams* p = k->p;
     if (is_halo(k, n)) return;
@@ -334,6 +355,44 @@ static void stream_collide_cell(const Ctx* k, const OraBuffers* b, uint32_t n, u
         float rhon_q = 0.0f;
         for (uint32_t i = 0u; i < 7u; i++) rhon_q += qhn[i];
         rhon_q += 1.0f;
+        if (p->subgrid_ecr) {  /* sim.cl:556-629 */
+            /* electron temperature 1 */
+            float ethn[7];
+            load_ddfs(k, 7u, n, ethn, b->eti, j7, t);
+            float Etn = 0.0f;
+            for (uint32_t i = 0u; i < 7u; i++) Etn += ethn[i];
+            Etn += 1.0f;
+            /* ECR heating */
+            const float Env[3] = {b->E_var[nxi], b->E_var[nyi], b->E_var[nzi]};
+            const float f_c = length3(Bn) * (1.0f / (p->kme * 2.0f * 3.14159274101257f));
+            /* `0.03125` and `32` are double / int literals: this term is evaluated in double and narrowed by sq(float) */
+            const float detune = (float)((double)p->ecrf / (0.03125 * (double)f_c) - 32);
+            const float rel_absorbtion = 1.0f / (1.0f + sq(detune));
+            (void)rel_absorbtion;  /* computed and printed by the reference, never used (sim.cl:584-585) */
+            const float sc = (Env[0] * Bn[0] + Env[1] * Bn[1] + Env[2] * Bn[2]) / sq(length3(Bn));
+            const float perp[3] = {Env[0] - sc * Bn[0], Env[1] - sc * Bn[1], Env[2] - sc * Bn[2]};
+            const float Env_mag = length3(perp);
+            Etn += p->keabs / p->kkbme * (rhon_e + 0.00001f) / p->kkge * sq(Env_mag);
+            /* drift of gyrating electrons */
+            float gr[3];
+            grad_mag_v(k, n, b->B_dyn, gr);
+            const float ke_t = p->kkbme * Etn, lb = length3(Bn);
+            const float dup[3] = {(ke_t * gr[0]) / lb, (ke_t * gr[1]) / lb, (ke_t * gr[2]) / lb};
+            uxn_e += dup[0];
+            uyn_e += dup[1];
+            uzn_e += dup[2];
+            Etn -= length3(dup) / p->kkbme;
+            /* electron temperature 2 */
+            float eteq[7];
+            calculate_a_eq(Etn, uxn_e, uyn_e, uzn_e, eteq);
+            if (p->update_fields) b->Et[n] = Etn;
+            for (uint32_t i = 0u; i < 7u; i++) ethn[i] = fmaf(1.0f - p->wq, ethn[i], p->wq * eteq[i]);
+            store_ddfs(k, 7u, n, ethn, b->eti, j7, t);
+            /* ionization */
+            const float delta_q_rho = 0.0001f * Etn;
+            rhon_e += delta_q_rho;
+            rhon_q += delta_q_rho;
+        }
         /* gas charge advection 2 */
         b->Q[n] = rhon_q - rhon_e;
         float qeq[7];
@@ -459,6 +518,11 @@ void ora_initialize(const OraParams* p, const OraBuffers* b) {
             b->E_dyn[nxi] = b->E_stat[nxi]; b->E_dyn[nyi] = b->E_stat[nyi]; b->E_dyn[nzi] = b->E_stat[nzi];
             calculate_f_eq(&k, 0.0f, b->u[nxi], b->u[nyi], b->u[nzi], fe_eq);  /* quirk Q10 */
             store_ddfs(&k, k.q, n, fe_eq, b->ei, j, 1ul);
+            if (p->subgrid_ecr) {  /* sim.cl:827-831 */
+                float eteq[7];
+                calculate_a_eq(b->Et[n], b->u[nxi], b->u[nyi], b->u[nzi], eteq);
+                store_ddfs(&k, 7u, n, eteq, b->eti, j7, 1ul);
+            }
         }
     }
 }

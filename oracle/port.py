@@ -44,12 +44,13 @@ class OraParams(ctypes.Structure):
                [(n, ctypes.c_uint32) for n in ("velocity_set", "trt", "float_type", "eq_boundaries", "volume_force",
                                                "force_field", "magneto_hydro", "update_fields")] + \
                [(n, ctypes.c_float) for n in ("w", "ke", "kmu", "kmu0", "kkge", "wq")] + \
-               [(n, ctypes.c_uint32) for n in ("lod_depth", "n_lod", "n_lod_own")] + [("threads", ctypes.c_int32)]
+               [(n, ctypes.c_uint32) for n in ("lod_depth", "n_lod", "n_lod_own")] + [("threads", ctypes.c_int32)] + \
+               [("subgrid_ecr", ctypes.c_uint32)] + [(n, ctypes.c_float) for n in ("kme", "kkbme", "keabs", "ecrf")]
 
 
 class OraBuffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in ("fi", "rho", "u", "flags", "F", "E_stat", "B_stat", "E_dyn", "B_dyn", "fqi",
-                                               "ei", "Q", "QU_lod", "transfer_p", "transfer_m")]
+                                               "ei", "Q", "QU_lod", "transfer_p", "transfer_m", "E_var", "eti", "Et")]
 
 
 _lib = None
@@ -118,6 +119,9 @@ def params_for(cfg: rh.RefConfig, g: rh.Geometry, threads=0) -> OraParams:
     p.wq = float(f32(f32(1.0) / f32(f32(f32(2.0) * u.k_charge_expansion_lu()) + f32(0.5))))
     p.lod_depth, p.n_lod, p.n_lod_own = cfg.mhd_lod_depth, g.n_lod, g.n_lod_own
     p.threads = threads
+    p.subgrid_ecr = int(cfg.ext_subgrid_ecr)
+    p.kme, p.kkbme, p.keabs = float(u.kme_lu()), float(u.kkBme_lu()), float(u.keabs_lu())
+    p.ecrf = float(f32(cfg.ecr_freq))
     return p
 
 
@@ -125,8 +129,6 @@ class PortDomain(rh.RefDomain):
     """LbmDomain (domain.rs:20-80) over the plain-C restatement."""
 
     def _load(self, lib_path=None):
-        if self.cfg.ext_subgrid_ecr:
-            raise NotImplementedError("SUBGRID_ECR is not restated (SURVEY section 8 row f3)")
         self.lib = lib()
         self.lib_path = LIB
         self.p = params_for(self.cfg, self.g, self.threads)
@@ -138,6 +140,7 @@ class PortDomain(rh.RefDomain):
         b.E_stat, b.B_stat, b.E_dyn, b.B_dyn = P(self.e_stat), P(self.b_stat), P(self.e_dyn), P(self.b_dyn)
         b.fqi, b.ei, b.Q, b.QU_lod = P(self.fqi), P(self.ei), P(self.qc), P(self.qu_lod)
         b.transfer_p, b.transfer_m = P(self.transfer_p), P(self.transfer_m)
+        b.E_var, b.eti, b.Et = P(self.e_var), P(self.eti), P(self.et)
         return ctypes.byref(self.p), ctypes.byref(b)
 
     def enqueue_initialize(self):
@@ -171,6 +174,9 @@ class PortDomain(rh.RefDomain):
 
     def enqueue_precompute_e(self):
         self.lib.ora_static_e_from_mesh(*self._pb(), self.e_stat.ctypes.data)
+
+    def enqueue_precompute_e_ecr(self):
+        self.lib.ora_static_e_from_mesh(*self._pb(), self.e_var.ctypes.data)
 
     def _voxelize(self, direction, flag, mpc):
         self.lib.ora_voxelize_mesh(*self._pb(), direction, flag, self.p0.ctypes.data, self.p1.ctypes.data,

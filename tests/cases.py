@@ -96,8 +96,28 @@ def multi_domain_mhd_cases():
     ]
 
 
+def _ecr(c, length=16.0):
+    """Units for the SUBGRID_ECR cases.  The extension is experimental in the reference (sim.cl:556-629: debug printfs, a
+    placeholder ionisation term, `a - b / 2.0f` in grad_mag_v) and with setup_deeva_test's units DEF_KKBME is ~ -1e12, so the
+    electron drift term overflows within two steps.  A velocity unit of 1e6 m/s per lattice unit brings DEF_KKBME to -2.3e-5
+    and keeps every field finite over the 8 recorded steps; the arithmetic exercised is the same."""
+    c.units.set(length, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0e6, 1.2250, 1e-10, 1.0)
+    return c
+
+
+def ecr_cases():
+    """SUBGRID_ECR: single domain only -- the reference never communicates `eti` (types.rs:105-111)."""
+    return [
+        ("ecr_d3q19_fp32", _ecr(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=12, n_z=8, nu=0.05, ext_volume_force=True,
+                                  ext_magneto_hydro=True, ext_subgrid_ecr=True, mhd_lod_depth=2, graphics_active=True, ecr_freq=2.0e-4))),
+        ("ecr_d3q27_fp16c_trt", _ecr(C(velocity_set="D3Q27", float_type="FP16C", relaxation_time="TRT", n_x=16, n_y=16, n_z=16, nu=0.05,
+                                       ext_volume_force=True, ext_magneto_hydro=True, ext_subgrid_ecr=True, mhd_lod_depth=3,
+                                       ecr_freq=2.0e-4))),
+    ]
+
+
 def all_cases():
-    return single_domain_cases() + mhd_cases() + multi_domain_cases() + multi_domain_mhd_cases()
+    return single_domain_cases() + mhd_cases() + multi_domain_cases() + multi_domain_mhd_cases() + ecr_cases()
 
 
 def fill_inputs(lbm, cfg, seed=1, smooth=False):
@@ -122,6 +142,11 @@ def fill_inputs(lbm, cfg, seed=1, smooth=False):
             d.qc[:] = (RHO_E0 + 0.002 + 0.0005 * rng.standard_normal(n)).astype(np.float32)
             d.b_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
             d.e_stat[:] = (1e-3 * rng.standard_normal(3 * n)).astype(np.float32)
+        if cfg.ext_subgrid_ecr:  # a nearly uniform guide field, a weak oscillating field and a temperature around 1
+            d.b_stat[:] = (1e-5 * rng.standard_normal(3 * n)).astype(np.float32)
+            d.b_stat[n:2 * n] += np.float32(0.01)
+            d.e_var[:] = (1e-13 * rng.standard_normal(3 * n)).astype(np.float32)
+            d.et[:] = (1.0 + 0.01 * rng.standard_normal(n)).astype(np.float32)
 
 
 # The reference initialises the electron gas at density 0 (initialize: calculate_f_eq(0.0, ...), quirk Q10); its first
@@ -171,7 +196,7 @@ def to_lbm_config(cfg, deterministic=False):
 
 # oracle buffer name -> product field id (include/ionsolver_b200.h enum IonField)
 FIELD_OF = {"fi": 0, "rho": 1, "u": 2, "flags": 3, "f": 4, "e_stat": 5, "b_stat": 6, "e_dyn": 7, "b_dyn": 8, "fqi": 9, "ei": 10,
-            "qc": 11, "qu_lod": 12, "transfer_p": 16, "transfer_m": 17}
+            "qc": 11, "qu_lod": 12, "e_var": 13, "eti": 14, "et": 15, "transfer_p": 16, "transfer_m": 17}
 
 
 def upload_inputs(ref_lbm, gpu_lbm):
@@ -183,5 +208,5 @@ def upload_inputs(ref_lbm, gpu_lbm):
         if cfg.ext_force_field:
             gd.write(FIELD_OF["f"], rd.f)
         if cfg.ext_magneto_hydro:
-            for name in ("qc", "b_stat", "e_stat"):
+            for name in ("qc", "b_stat", "e_stat") + (("e_var", "et") if cfg.ext_subgrid_ecr else ()):
                 gd.write(FIELD_OF[name], getattr(rd, name))

@@ -48,6 +48,8 @@ def buffers_of(d, cfg):
         names += ["transfer_p", "transfer_m"]
     if cfg.ext_magneto_hydro:
         names += ["ei", "fqi", "qc", "e_dyn", "b_dyn", "qu_lod"]
+    if cfg.ext_subgrid_ecr:
+        names += ["eti", "et"]
     return {n: digest(getattr(d, n)) for n in names}
 
 

@@ -19,6 +19,8 @@ def buffer_names(cfg):
         names += ["transfer_p", "transfer_m"]
     if cfg.ext_magneto_hydro:
         names += ["ei", "fqi", "qc", "e_dyn", "b_dyn", "qu_lod"]
+    if cfg.ext_subgrid_ecr:
+        names += ["eti", "et"]
     return names
 
 

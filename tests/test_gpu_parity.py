@@ -110,7 +110,7 @@ def test_mhd_single_step_parity(name, cfg, golden, gpu_lib):
     gpu.close()
 
 
-ALL_MHD = cases.mhd_cases() + cases.multi_domain_mhd_cases()
+ALL_MHD = cases.mhd_cases() + cases.multi_domain_mhd_cases() + cases.ecr_cases()
 
 
 @pytest.mark.parametrize("name,cfg", ALL_MHD, ids=[c[0] for c in ALL_MHD])
@@ -388,7 +388,7 @@ def test_error_behaviour(gpu_lib):
     plain.close()
     bad = [dict(ext_magneto_hydro=True),                                              # MHD without VOLUME_FORCE does not compile in the reference
            dict(ext_magneto_hydro=True, ext_volume_force=True, mhd_lod_depth=5),      # 1<<(1<<5) shifts out of range
-           dict(ext_magneto_hydro=True, ext_volume_force=True, ext_subgrid_ecr=True)]  # SURVEY 8 row f3, not built yet
+           dict(ext_volume_force=True, ext_subgrid_ecr=True)]                          # SUBGRID_ECR lives inside the MHD block
     for kw in bad:
         with pytest.raises(capi.IonError) as e:
             L.Lbm(L.LbmConfig(velocity_set=L.VelocitySet.D3Q19, float_type=L.FloatType.FP32, n_x=32, n_y=32, n_z=32, **kw), devices=[0])

@@ -78,8 +78,11 @@ def test_make_params_matches_get_device_defines(name, cfg):
                              ("DEF_KVEV", p.kvev), ("DEF_KME", p.kme), ("DEF_WQ", p.wq)):
                 assert np.float32(val) == lit(key), key
         ext = (1 * cfg.ext_equilibrium_boudaries | 2 * cfg.ext_volume_force | 4 * cfg.ext_force_field | 8 * cfg.ext_magneto_hydro
-               | 32 * cfg.graphics_active)
+               | 16 * cfg.ext_subgrid_ecr | 32 * cfg.graphics_active)
         assert p.ext == ext
+        if cfg.ext_subgrid_ecr:
+            for key, val in (("DEF_KKBME", p.kkbme), ("DEF_KEABS", p.keabs)):
+                assert np.float32(val) == lit(key), key
 
 
 def test_lod_counts_of_the_reference_scenes():
