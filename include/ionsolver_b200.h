@@ -213,6 +213,9 @@ ION_API int ion_comm_exchange_lods(ion_comm_t* comm, ion_domain_t* d);
 
 /* instrumentation (no reference equivalent): kernels launched by this library since load, for bench.py */
 ION_API uint64_t ion_kernel_launch_count(void);
+/* DDF storage codec on the device (test hook; the macros load/store of domain.rs:773-784, sim_kernels.cl:79-90):
+ * dir 0: count floats -> count storage words (u16 or f32), dir 1: storage words -> floats.  Host pointers. */
+ION_API int ion_codec_probe(int device, int float_type, int dir, const void* host_in, void* host_out, uint64_t count);
 /* FP32 issue-peak probe (FMA/s of the whole device; packed = fma.rn.f32x2): the compute roofline of update_e_b_dynamic */
 ION_API int ion_measure_fma_peak(int device, int packed, double* fma_per_s);
 /* the CUDA stream of a domain (cudaStream_t as void*), so callers can record CUDA events on it */

@@ -47,7 +47,7 @@ SYMBOLS = [
     "ion_kernel_launch_count", "ion_domain_stream",
     "ion_exchange_transfer", "ion_copy_lods", "ion_comm_unique_id", "ion_comm_create", "ion_comm_destroy",
     "ion_comm_exchange_transfer", "ion_comm_exchange_lods", "ion_neighbor_domains", "ion_lod_exchange_plan",
-    "ion_measure_fma_peak", "ion_halo_fork", "ion_halo_join",
+    "ion_measure_fma_peak", "ion_halo_fork", "ion_halo_join", "ion_codec_probe",
 ]
 # every symbol include/ionsolver_b200_host.h declares
 HOST_SYMBOLS = [
@@ -161,6 +161,7 @@ def load() -> ctypes.CDLL:
     L.ion_lod_exchange_plan.argtypes = [c.POINTER(IonParams), c.c_uint32, U32P, U32P, U32P]
     L.ion_halo_fork.argtypes = [D]
     L.ion_halo_join.argtypes = [D]
+    L.ion_codec_probe.argtypes = [c.c_int, c.c_int, c.c_int, c.c_void_p, c.c_void_p, c.c_uint64]
     L.ion_measure_fma_peak.argtypes = [c.c_int, c.c_int, c.POINTER(c.c_double)]
     # ---- host layer (include/ionsolver_b200_host.h) ----
     CFG = c.POINTER(IonLbmConfig)
@@ -350,3 +351,16 @@ def measure_fma_peak(device=0, packed=False) -> float:
     v = ctypes.c_double()
     check(load().ion_measure_fma_peak(device, int(packed), ctypes.byref(v)))
     return v.value
+
+
+def codec_probe(float_type, arr, direction, device=0):
+    """DDF storage codec on the device: direction 0 float32 -> stored words, 1 stored words -> float32."""
+    import numpy as np
+    if direction == 0:
+        a = np.ascontiguousarray(arr, np.float32)
+        out = np.empty(a.size, np.float32 if float_type == 2 else np.uint16)
+    else:
+        a = np.ascontiguousarray(arr, np.float32 if float_type == 2 else np.uint16)
+        out = np.empty(a.size, np.float32)
+    check(load().ion_codec_probe(device, float_type, direction, a.ctypes.data, out.ctypes.data, a.size))
+    return out

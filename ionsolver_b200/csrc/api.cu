@@ -57,6 +57,15 @@ template <bool PACKED> __global__ void __launch_bounds__(256) k_fma_peak(float* 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DDF storage codec probe (test hook, like ref_codec of the oracle driver): dir 0 float -> stored, 1 stored -> float
+template <int FP> __global__ void k_codec(const void* in, void* out, uint64_t count, int dir) {
+    typedef typename Codec<FP>::store_t S;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    if (dir == 0) reinterpret_cast<S*>(out)[i] = Codec<FP>::enc(reinterpret_cast<const float*>(in)[i]);
+    else reinterpret_cast<float*>(out)[i] = Codec<FP>::dec(reinterpret_cast<const S*>(in)[i]);
+}
+
 __global__ void k_fill_f32(float* p, uint64_t n, float v) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -100,6 +109,30 @@ extern "C" {
 const char* ion_last_error_string(void) { return g_err; }
 uint32_t ion_abi_version(void) { return ION_ABI_VERSION; }
 uint64_t ion_kernel_launch_count(void) { return g_launches.load(); }
+
+int ion_codec_probe(int device, int float_type, int dir, const void* host_in, void* host_out, uint64_t count) {
+    if (!host_in || !host_out) return fail(ION_ERR_INVALID, "NULL argument");
+    if (float_type < ION_FP16S || float_type > ION_FP32 || dir < 0 || dir > 1) return fail(ION_ERR_INVALID, "bad float_type / dir");
+    ION_CUDA(cudaSetDevice(device));
+    const size_t ss = float_type == ION_FP32 ? 4 : 2;
+    const size_t in_b = count * (dir == 0 ? 4 : ss), out_b = count * (dir == 0 ? ss : 4);
+    void *din = nullptr, *dout = nullptr;
+    ION_CUDA(cudaMalloc(&din, in_b ? in_b : 1));
+    ION_CUDA(cudaMalloc(&dout, out_b ? out_b : 1));
+    ION_CUDA(cudaMemcpy(din, host_in, in_b, cudaMemcpyHostToDevice));
+    const unsigned grid = (unsigned)((count + 255) / 256);
+    if (count) {
+        if (float_type == ION_FP32) k_codec<ION_FP32><<<grid, 256>>>(din, dout, count, dir);
+        else if (float_type == ION_FP16S) k_codec<ION_FP16S><<<grid, 256>>>(din, dout, count, dir);
+        else k_codec<ION_FP16C><<<grid, 256>>>(din, dout, count, dir);
+        g_launches++;
+    }
+    cudaError_t e = cudaMemcpy(host_out, dout, out_b, cudaMemcpyDeviceToHost);
+    cudaFree(din);
+    cudaFree(dout);
+    if (e != cudaSuccess) return cuda_fail(e, "codec probe");
+    return ION_OK;
+}
 
 int ion_measure_fma_peak(int device, int packed, double* fma_per_s) {
     if (!fma_per_s) return fail(ION_ERR_INVALID, "NULL argument");

@@ -267,6 +267,26 @@ __global__ void __launch_bounds__(EBT_BLOCK) k_update_e_b_tiled(const __grid_con
         s_tab[k] = v;
     }
     __syncthreads();
+    // Rows of the source grid whose ND entries are all zero (no charge in those LOD blocks) add exactly nothing: flag them
+    // once per block and skip them in the row loop (warp-uniform).  Single-domain runs always have such rows: the window
+    // [NUM_LOD_OWN - 8^D, NUM_LOD_OWN) of quirk Q5 ends in 8^0 + ... + 8^(D-1) coarse-level slots that nothing ever fills.
+    // The deterministic path visits every row (adding a zero can flip the sign of a -0 accumulator).
+    __shared__ uint8_t s_nz[ND * ND + 2];
+    {
+        const uint32_t r_lo = lo / ND, n_rows = (a.n_lod_own + ND - 1) / ND - r_lo;
+        for (uint32_t r = threadIdx.x; r < n_rows; r += EBT_BLOCK) {
+            bool nz = EXACT;
+            const int d0 = (int)((r_lo + r) * ND) - (int)lo;
+            for (int cx = 0; cx < ND && !nz; cx++) {
+                const int slot = d0 + cx;
+                if (slot < 0 || slot >= (int)cnt) continue;
+                const float4 v = s_tab[slot];
+                nz = v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f;
+            }
+            s_nz[r] = nz ? 1 : 0;
+        }
+    }
+    __syncthreads();
     const uint32_t dsx = a.nx / ND, dsy = a.ny / ND, dsz = a.nz / ND;
     const uint32_t m = blockIdx.x * EBT_BLOCK + threadIdx.x;  // (ox, y) of this thread, z = blockIdx.y
     if (m >= dsx * a.ny) return;
@@ -316,6 +336,7 @@ __global__ void __launch_bounds__(EBT_BLOCK) k_update_e_b_tiled(const __grid_con
     const float rx0 = (float)ox - 0.5f * dsxf;  // r_x for block difference 0: (k*dsx+ox) - (cx*dsx + dsx/2), k == cx
     const uint32_t row_lo = lo / ND, row_hi = (a.n_lod_own + ND - 1) / ND;
     for (uint32_t row = row_lo; row < row_hi; row++) {
+        if (!s_nz[row - row_lo]) continue;  // no charge in this row of LOD blocks
         const uint32_t cy = row % ND, cz = row / ND;
         const float ry = fy - ((float)cy * dsyf + 0.5f * dsyf);
         const float rz = fz - ((float)cz * dszf + 0.5f * dszf);
@@ -475,6 +496,22 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
         s_pair[2u * k + 1u] = make_float4(v0.z * v0.x, v1.z * v1.x, v0.w * v0.x, v1.w * v1.x);
     }
     __syncthreads();
+    __shared__ uint8_t s_nz[ND * ND + 2];  // rows without any charge are skipped, see k_update_e_b_tiled
+    {
+        const uint32_t r_lo = lo / ND, n_rows = (a.n_lod_own + ND - 1) / ND - r_lo;
+        for (uint32_t r = threadIdx.x; r < n_rows; r += BLOCK) {
+            bool nz = false;
+            const int d0 = (int)((r_lo + r) * ND) - (int)lo;
+            for (int cx = 0; cx < ND && !nz; cx++) {
+                const int slot = d0 + cx;
+                if (slot < 0 || slot >= (int)cnt) continue;
+                const float4 A = s_pair[2 * slot], B = s_pair[2 * slot + 1];
+                nz = A.x != 0.0f || A.z != 0.0f || B.x != 0.0f || B.z != 0.0f;
+            }
+            s_nz[r] = nz ? 1 : 0;
+        }
+    }
+    __syncthreads();
     const uint32_t dsx = a.nx / ND, dsy = a.ny / ND, dsz = a.nz / ND;
     const uint32_t m = blockIdx.x * BLOCK + threadIdx.x;  // (ox, part, y) of this thread, z = blockIdx.y
     if (m >= dsx * PARTS * a.ny) return;
@@ -524,6 +561,7 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
     const float rx0 = (float)(kbase * dsx + ox) - 0.5f * dsxf;  // r_x of cell kl = 0 against source c = 0
     const uint32_t row_lo = lo / ND, row_hi = (a.n_lod_own + ND - 1) / ND;
     for (uint32_t row = row_lo; row < row_hi; row++) {
+        if (!s_nz[row - row_lo]) continue;  // no charge in this row of LOD blocks
         const uint32_t cy = row % ND, cz = row / ND;
         const float ry = fy - ((float)cy * dsyf + 0.5f * dsyf);
         const float rz = fz - ((float)cz * dszf + 0.5f * dszf);
@@ -616,10 +654,14 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
                 const float ryz2 = fmaf(ry, ry, rz * rz);
                 float4 src[NF];
 #pragma unroll
+                bool nz = false;
+#pragma unroll
                 for (int cx = 0; cx < NF; cx++) {
                     const float4 v = __ldg(lod + row * NF + cx);
                     src[cx] = make_float4(v.x, v.y * v.x, v.z * v.x, v.w * v.x);
+                    nz = nz || src[cx].x != 0.0f || src[cx].y != 0.0f || src[cx].z != 0.0f || src[cx].w != 0.0f;
                 }
+                if (!nz) continue;  // same for every thread: the row holds no charge
 #pragma unroll
                 for (int m = -(NF - 1); m < NC / 2; m++) {
                     const float2 rx = make_float2((float)(2 * m - 1) * dsxf + rxb, (float)(2 * m) * dsxf + rxb);

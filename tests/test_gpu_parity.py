@@ -74,6 +74,33 @@ def test_single_domain_bit_exact(name, cfg, golden, gpu_lib):
     gpu.close()
 
 
+def test_codecs_exhaustive(gpu_lib):
+    """FP16S / FP16C storage codecs on the device against the oracle (whose codecs are pinned to the reference's by the golden
+    vectors): every one of the 65 536 codes decodes to the same float, and 2^22 random floats plus the special values (zeros,
+    denormal range of both formats, rounding ties, overflow wrap of FP16C, +-2) encode to the same code."""
+    from ionsolver_b200 import capi
+    codes = np.arange(65536, dtype=np.uint16)
+    rng = np.random.default_rng(11)
+    x = np.concatenate([
+        (rng.standard_normal(1 << 21) * np.exp(rng.uniform(-20, 1, 1 << 21))).astype(np.float32),
+        rng.uniform(-2.5, 2.5, 1 << 21).astype(np.float32),
+        np.array([0.0, -0.0, 1.0, -1.0, 1.9990234, 2.0, -2.0, 3.0, 6.1035156e-05, 3.0517578e-05, 2.9802322e-08, 1e-9, 65504.0 / 32768.0],
+                 np.float32),
+        (codes.astype(np.float32) / 2048.0 * np.float32(2.0 ** -14)).astype(np.float32),  # FP16C denormal grid incl. ties
+    ])
+    for ft, name in ((0, "FP16S"), (1, "FP16C")):
+        cfg = rh.RefConfig(velocity_set="D3Q19", float_type=name, n_x=4, n_y=4, n_z=4)
+        dom = rh.RefLbm(cfg, threads=1, backend="port").domains[0]
+        want_dec = dom.codec(codes, 1)
+        got_dec = capi.codec_probe(ft, codes, 1)
+        nan = np.isnan(want_dec)  # FP16S has 2046 NaN codes: they decode to NaN on both sides, payloads are not compared
+        assert (np.isnan(got_dec) == nan).all()
+        assert same_bits(got_dec[~nan], want_dec[~nan]), f"{name} decode: {int((got_dec.view(np.uint32) != want_dec.view(np.uint32))[~nan].sum())} codes differ"
+        want_enc = dom.codec(x, 0)
+        got_enc = capi.codec_probe(ft, x, 0)
+        assert same_bits(got_enc, want_enc), f"{name} encode: {int((got_enc != want_enc).sum())} values differ"
+
+
 MHD = cases.mhd_cases()
 
 
