@@ -653,7 +653,6 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
                 const float rz = fz - (((float)cz * bsz + 0.5f * bsz) - fd.sz);
                 const float ryz2 = fmaf(ry, ry, rz * rz);
                 float4 src[NF];
-#pragma unroll
                 bool nz = false;
 #pragma unroll
                 for (int cx = 0; cx < NF; cx++) {
