@@ -19,6 +19,7 @@ cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt,
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
 cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, bool exact);
+cudaError_t launch_lod_fold(const KArgs& a, cudaStream_t s);
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di);
 cudaError_t launch_clear_qu_lod(const KArgs& a, cudaStream_t s);
 cudaError_t launch_lod_deposit_ordered(const KArgs& a, cudaStream_t s);
@@ -274,6 +275,12 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
             e = cudaMalloc((void**)&d->lod_u, n * 12);
             if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc lod_u"); }
         }
+        if (!deterministic && p->lod_depth > 0u) {  // private replicas of the finest LOD level for the deposit (stream_collide.cuh)
+            const size_t rep_bytes = (size_t)ION_LOD_REPLICAS * ((size_t)1 << (3u * p->lod_depth)) * 16u;
+            e = cudaMalloc((void**)&d->lod_rep, rep_bytes);
+            if (e == cudaSuccess) e = cudaMemset(d->lod_rep, 0, rep_bytes);
+            if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc lod_rep"); }
+        }
         e = cudaMalloc(&d->lod_sources, lod_source_bytes(p->lod_depth, p->n_lod_own, p->dx, p->dy, p->dz, p->di));
         if (e == cudaSuccess) e = cudaMalloc((void**)&d->cp_counts, compaction_scratch_bytes(n));
         if (e != cudaSuccess) { ion_domain_destroy(d); return cuda_fail(e, "cudaMalloc scratch"); }
@@ -294,6 +301,9 @@ int ion_domain_create(const IonParams* p, int device, ion_domain_t** out) {
     k.Q = (float*)d->buf[ION_FIELD_Q];
     k.QU_lod = (float*)d->buf[ION_FIELD_QU_LOD];
     k.lod_u = d->lod_u;
+    k.lod_rep = d->lod_rep;
+    k.lod_rep_mask = ION_LOD_REPLICAS - 1u;
+    k.lod_rep_entries = d->lod_rep ? (1u << (3u * p->lod_depth)) : 0u;
     d->deterministic = deterministic;
     k.E_var = (const float*)d->buf[ION_FIELD_E_VAR];
     k.eti = d->buf[ION_FIELD_ETI];
@@ -325,6 +335,7 @@ int ion_domain_destroy(ion_domain_t* d) {
     if (d->lod_sources) cudaFree(d->lod_sources);
     if (d->cp_counts) cudaFree(d->cp_counts);
     if (d->lod_u) cudaFree(d->lod_u);
+    if (d->lod_rep) cudaFree(d->lod_rep);
     if (d->alt_p) cudaFree(d->alt_p);
     if (d->alt_m) cudaFree(d->alt_m);
     if (d->lod_gather) cudaFree(d->lod_gather);
@@ -445,6 +456,10 @@ int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, 
         e = launch_lod_deposit_ordered(d->k, d->stream);
         g_launches++;
         if (e != cudaSuccess) return cuda_fail(e, "lod_deposit_ordered launch");
+    } else if (mhd && d->lod_rep) {  // replicas of the finest level -> QU_lod (the reference's atomics land there directly)
+        e = launch_lod_fold(d->k, d->stream);
+        g_launches++;
+        if (e != cudaSuccess) return cuda_fail(e, "lod_fold launch");
     }
     return ION_OK;
 }

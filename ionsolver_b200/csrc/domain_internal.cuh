@@ -18,6 +18,7 @@ struct ion_domain {
     void* alt_p;          // spare transfer buffers: receive side of peer copies / NCCL (see ion_exchange_transfer)
     void* alt_m;
     float* lod_u;         // deterministic mode: per-cell velocity deposits (3N floats)
+    float* lod_rep;       // default mode: ION_LOD_REPLICAS private copies of the finest LOD level (deposit target of stream_collide)
     float* lod_gather;    // world * n_lod_own * 4 floats, allocated on first ion_comm_exchange_lods
     cudaEvent_t ev;       // reusable ordering event (timing disabled)
     // halo stream: between ion_halo_fork and ion_halo_join the transfer kernels and the face exchange of this domain run
@@ -28,6 +29,10 @@ struct ion_domain {
     float ecrf;
     bool deterministic;   // ION_EXT_DETERMINISTIC: reference-ordered LOD sums and reference arithmetic in update_e_b_dynamic
 };
+
+#ifndef ION_LOD_REPLICAS
+#define ION_LOD_REPLICAS 32u  // power of two
+#endif
 
 namespace ion {
 extern std::atomic<uint64_t> g_launches;

@@ -732,6 +732,30 @@ cudaError_t launch_lod_deposit_ordered(const KArgs& a, cudaStream_t s) {
     return cudaGetLastError();
 }
 
+// Folds the private replicas of the finest LOD level (stream_collide.cuh, lod_deposit_warp) into QU_lod and clears them for
+// the next step.  One thread per (entry, component): 8^depth * 4 threads, lod_rep_count coalesced reads each.
+__global__ void k_lod_fold(const __grid_constant__ KArgs a, uint32_t own_offset) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t words = a.lod_rep_entries * 4u;
+    if (t >= words) return;
+    float s = 0.0f;
+    for (uint32_t r = 0; r <= a.lod_rep_mask; r++) {
+        float* p = a.lod_rep + (size_t)r * words + t;
+        s += *p;
+        *p = 0.0f;
+    }
+    const uint32_t entry = (t >> 2) + own_offset;
+    if (entry < a.n_lod) a.QU_lod[(size_t)entry * 4u + (t & 3u)] += s;
+}
+cudaError_t launch_lod_fold(const KArgs& a, cudaStream_t s) {
+    uint32_t off = 0u;
+    if (a.dx > 1u || a.dy > 1u || a.dz > 1u)
+        for (uint32_t d = 0u; d < a.lod_depth; d++) off += 1u << (d * 3u);  // sim.cl:667-670 (to_d of the 3-D sets)
+    const uint32_t words = a.lod_rep_entries * 4u;
+    k_lod_fold<<<(words + 127u) / 128u, 128, 0, s>>>(a, off);
+    return cudaGetLastError();
+}
+
 // clear_qu_lod, sim.cl:995-1003: global size n_lod (domain.rs:277), guard n > NUM_LOD_OWN (quirk Q12)
 __global__ void k_clear_qu_lod(float* __restrict__ QU_lod, uint32_t n_lod, uint32_t n_lod_own) {
     const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;

@@ -31,6 +31,9 @@ struct KArgs {
     float* Q;
     float* QU_lod;
     float* lod_u;  // deterministic mode: per-cell scaled velocity deposit (3N floats), summed in order by k_lod_deposit_ordered
+    float* lod_rep;             // privatised LOD deposit: lod_rep_count replicas of the own finest level (8^depth float4 each)
+    uint32_t lod_rep_mask;      // lod_rep_count - 1 (power of two)
+    uint32_t lod_rep_entries;   // 8^depth
     const float* E_var;
     void* eti;
     float* Et;
@@ -115,7 +118,20 @@ template <int VS> __device__ __forceinline__ float cdot(int i, float ax, float a
 // ------------------------------------------------------------------------------------------------------
 // DDF storage codecs: FP32 plain, FP16S (domain.rs:773-776), FP16C (sim.cl:79-90)
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint16_t fp16c_encode(float x) {  // 1-4-11 custom format
+// float_to_half_custom, sim.cl:79-84 (1-4-11 format).  The reference rounds the mantissa by adding 0x800 to the float's bits,
+// then assembles exponent and mantissa fields, with a separate shift-and-round path for results below 2^-14 (~20 integer
+// operations).  The same bits come out of ONE multiplication: |x| * 2^-112 re-biases the exponent (127 -> 15) exactly for
+// normal results and, rounded TOWARD ZERO, lands results below 2^-14 on the float-denormal grid, which is the reference's
+// truncating shift; adding 0x800 to those bits and dropping 12 bits is then its round-half-up in both ranges (mantissa
+// carries ripple into the exponent field like in the reference, the 4-bit exponent wraps the same way, +-inf included).
+// Checked against fp16c_encode_ref for every non-NaN float on the CPU (2^32 - 2^24 inputs, round-toward-zero emulation) and
+// on the device in tests/test_gpu_parity.py::test_codecs_exhaustive.  NaN inputs (a broken simulation) give a different
+// finite code than the reference's bit shuffle.
+__device__ __forceinline__ uint16_t fp16c_encode(float x) {
+    const uint32_t a = __float_as_uint(__fmul_rz(fabsf(x), 1.925929944387236e-34f)) + 0x00000800u;  // 2^-112
+    return (uint16_t)(((a >> 12) & 0x7FFFu) | ((__float_as_uint(x) >> 16) & 0x8000u));
+}
+__device__ __forceinline__ uint16_t fp16c_encode_ref(float x) {  // the reference's formula, kept for the codec test hook
     const uint32_t b = __float_as_uint(x) + 0x00000800u;
     const uint32_t e = (b & 0x7F800000u) >> 23;
     const uint32_t m = b & 0x007FFFFFu;
@@ -214,6 +230,37 @@ __device__ __forceinline__ uint32_t neighbor7(const Cell& c, int i) {
 #ifndef ION_DDF_HINT
 #define ION_DDF_HINT 0
 #endif
+// ION_SPEC_LOADS = 1: DDF / field loads of stream_collide are `asm volatile`, which pins them in program order BEFORE the
+// branch on the cell's flag byte.  With plain C++ loads nvcc sinks all of them below that branch (their values are dead on
+// the solid path), so a warp first waits one full HBM round trip for one byte per cell with nothing else in flight.
+#ifndef ION_SPEC_LOADS
+#define ION_SPEC_LOADS 1
+#endif
+#if ION_SPEC_LOADS == 2
+#define ION_LD_PIN "ld.relaxed.gpu.global"
+#elif ION_SPEC_LOADS == 3
+#define ION_LD_PIN "ld.global"
+#else
+#define ION_LD_PIN "ld.volatile.global"
+#endif
+__device__ __forceinline__ float ld_f32_pinned(const float* p) {
+#if ION_SPEC_LOADS
+    float v;
+    asm volatile(ION_LD_PIN ".f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+#else
+    return *p;
+#endif
+}
+__device__ __forceinline__ uint8_t ld_u8_pinned(const uint8_t* p) {
+#if ION_SPEC_LOADS
+    uint16_t v;
+    asm volatile(ION_LD_PIN ".u8 %0, [%1];" : "=h"(v) : "l"(p));
+    return (uint8_t)v;
+#else
+    return *p;
+#endif
+}
 template <typename S> __device__ __forceinline__ S ddf_ld(const S* p) {
 #if ION_DDF_HINT == 1
     return __ldcs(p);
@@ -221,6 +268,14 @@ template <typename S> __device__ __forceinline__ S ddf_ld(const S* p) {
     return *p;
 #endif
 }
+#if ION_SPEC_LOADS && ION_DDF_HINT == 0
+template <> __device__ __forceinline__ float ddf_ld<float>(const float* p) { return ld_f32_pinned(p); }
+template <> __device__ __forceinline__ uint16_t ddf_ld<uint16_t>(const uint16_t* p) {
+    uint16_t v;
+    asm volatile(ION_LD_PIN ".u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return v;
+}
+#endif
 template <typename S> __device__ __forceinline__ void ddf_st(S* p, S v) {
 #if ION_DDF_HINT == 1
     __stcs(p, v);
@@ -248,6 +303,35 @@ __device__ __forceinline__ void ep_store(const float* f, void* buf, uint64_t N, 
     for (int i = 1; i < QQ; i += 2) {
         ddf_st(p + ((uint64_t)(i + (int)todd) * N + nb(i)), Codec<FP>::enc(f[i]));          // t odd ? i+1 : i
         ddf_st(p + ((uint64_t)(i + 1 - (int)todd) * N + n), Codec<FP>::enc(f[i + 1]));      // t odd ? i : i+1
+    }
+}
+
+// Compile-time parity variants (ODD = t & 1) used by stream_collide: every slot index is a constant, and each address is
+// formed as (64-bit pointer of the cell or of its neighbour) + (warp-uniform slot offset), i.e. two integer instructions per
+// access.  With a run-time parity the slot offsets (i + 1 - todd) * N are 64-bit run-time products and the address arithmetic
+// was ~40 % of the kernel's instructions (SASS of the FP32 MHD kernel: 620 integer/uniform instructions for 90 accesses).
+template <int FP, int QQ, bool ODD, typename NB>
+__device__ __forceinline__ void ep_load_p(float* f, const void* buf, uint64_t N, uint32_t n, NB nb) {
+    typedef typename Codec<FP>::store_t S;
+    const S* p = reinterpret_cast<const S*>(buf);
+    const S* pn = p + n;
+    f[0] = Codec<FP>::dec(ddf_ld(pn));
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        f[i] = Codec<FP>::dec(ddf_ld(pn + (uint64_t)(ODD ? i : i + 1) * N));               // t odd ? i : i+1
+        f[i + 1] = Codec<FP>::dec(ddf_ld((p + nb(i)) + (uint64_t)(ODD ? i + 1 : i) * N));   // t odd ? i+1 : i
+    }
+}
+template <int FP, int QQ, bool ODD, typename NB>
+__device__ __forceinline__ void ep_store_p(const float* f, void* buf, uint64_t N, uint32_t n, NB nb) {
+    typedef typename Codec<FP>::store_t S;
+    S* p = reinterpret_cast<S*>(buf);
+    S* pn = p + n;
+    ddf_st(pn, Codec<FP>::enc(f[0]));
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        ddf_st((p + nb(i)) + (uint64_t)(ODD ? i + 1 : i) * N, Codec<FP>::enc(f[i]));        // t odd ? i+1 : i
+        ddf_st(pn + (uint64_t)(ODD ? i : i + 1) * N, Codec<FP>::enc(f[i + 1]));             // t odd ? i : i+1
     }
 }
 
@@ -311,6 +395,134 @@ __device__ __forceinline__ void forcing_terms(float ux, float uy, float uz, floa
 #pragma unroll
     for (int i = 1; i < QQ; i++) {
         Fin[i] = (9.0f * wdir<VS>(i)) * fmaf(cdot<VS>(i, fx, fy, fz), cdot<VS>(i, ux, uy, uz) + 0.33333334f, uF);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Two-species packed arithmetic for the MHD kernel.  The neutral gas (fi) and the electron gas (ei) go through the SAME
+// moment / equilibrium / Guo-forcing / SRT-relaxation formulas on the same lattice (sim.cl:208-233,155-207,367-377,649-655
+// and 712-723), so they are evaluated together in the two lanes of sm_100's packed FP32 instructions (add/mul/fma.rn.f32x2):
+// lane .x = gas, lane .y = electrons.  Each lane is an independent IEEE round-to-nearest operation, so every value is
+// bit-identical to the scalar sequence; the instruction count of these blocks halves.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 splat2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+
+template <int VS> __device__ __forceinline__ float2 cdot2(int i, float2 ax, float2 ay, float2 az) {  // cdot, both lanes
+    const int cx = cvel<VS>(0, i), cy = cvel<VS>(1, i), cz = cvel<VS>(2, i);
+    float2 s = make_float2(0.0f, 0.0f);
+    bool first = true;
+    if (cx != 0) { s = cx > 0 ? ax : neg2(ax); first = false; }
+    if (cy != 0) { const float2 t = cy > 0 ? ay : neg2(ay); s = first ? t : add2(s, t); first = false; }
+    if (cz != 0) { const float2 t = cz > 0 ? az : neg2(az); s = first ? t : add2(s, t); first = false; }
+    return s;
+}
+
+// calculate_rho_u for both species: density and MOMENTUM sums (the three divisions stay scalar at the caller)
+template <int VS> __device__ __forceinline__ void rho_m2(const float* f, const float* e, float2& rho, float2 (&m)[3]) {
+    constexpr int QQ = VSet<VS>::Q;
+    float2 r = make_float2(f[0], e[0]);
+#pragma unroll
+    for (int i = 1; i < QQ; i++) r = add2(r, make_float2(f[i], e[i]));
+    rho = add2(r, splat2(1.0f));
+#pragma unroll
+    for (int ax = 0; ax < 3; ax++) {
+        m[ax] = make_float2(0.0f, 0.0f);
+        bool first = true;
+#pragma unroll
+        for (int i = 1; i < QQ; i += 2) {
+            const int c = cvel<VS>(ax, i);
+            if (c != 0) {
+                const float2 plus = c > 0 ? make_float2(f[i], e[i]) : make_float2(f[i + 1], e[i + 1]);
+                const float2 minus = c > 0 ? make_float2(f[i + 1], e[i + 1]) : make_float2(f[i], e[i]);
+                m[ax] = first ? plus : add2(m[ax], plus);
+                m[ax] = add2(m[ax], neg2(minus));  // a - b == a + (-b) exactly
+                first = false;
+            }
+        }
+    }
+}
+
+// TRT relaxation of one direction pair (i, i+1) of the gas, sim.cl:725-755 restricted to the pair (the scheme only couples
+// a direction with its opposite).  vf: Guo terms are split into symmetric / antisymmetric parts first (sim.cl:731-741).
+__device__ __forceinline__ void trt_pair(float& fa, float& fb, float qa, float qb, float Fa, float Fb, float wp, float wm, bool vf) {
+    if (vf) {
+        const float c_taup = fmaf(wp, -0.25f, 0.5f), c_taum = fmaf(wm, -0.25f, 0.5f);
+        const float Fa2 = fmaf(c_taup, Fa + Fb, c_taum * (Fa - Fb)), Fb2 = fmaf(c_taup, Fb + Fa, c_taum * (Fb - Fa));
+        Fa = Fa2;
+        Fb = Fb2;
+    }
+    const float na = fmaf(0.5f * wp, qa - fa + qb - fb, fmaf(0.5f * wm, qa - qb - fa + fb, fa + Fa));
+    const float nb = fmaf(0.5f * wp, qb - fb + qa - fa, fmaf(0.5f * wm, qb - qa - fb + fa, fb + Fb));
+    fa = na;
+    fb = nb;
+}
+
+// Equilibrium + Guo forcing + relaxation of both species, one direction pair at a time so that neither feq[] nor Fin[] is
+// ever materialised (the scalar code keeps 2*Q of them live).  rho/u/F: lane .x gas, lane .y electrons; u is the
+// force-corrected, clamped velocity.  Gas: SRT or TRT (template), forcing only if vf; electrons: always SRT with forcing
+// (sim.cl:641-656).  is_e: TYPE_E cell under EQUILIBRIUM_BOUNDARIES -> both populations are set to their equilibrium.
+template <int VS, bool TRT>
+__device__ __forceinline__ void collide_two_species(float* f, float* e, float2 rho, float2 ux, float2 uy, float2 uz, float2 Fx, float2 Fy, float2 Fz,
+                                                    float w, bool vf, bool is_e) {
+    constexpr int QQ = VSet<VS>::Q;
+    const float c_tau = fmaf(w, -0.5f, 1.0f);  // sim.cl:519
+    const float wm = TRT ? 1.0f / (0.1875f / (1.0f / w - 0.5f) + 0.5f) : 0.0f;
+    const float2 W = splat2(w), W1 = splat2(1.0f - w), CT = splat2(c_tau), HALF = splat2(0.5f), THIRD = splat2(0.33333334f);
+    // forcing_terms, sim.cl:367-377
+    const float2 uF = VS == ION_D2Q9 ? mul2(splat2(-0.33333334f), fma2(ux, Fx, mul2(uy, Fy)))
+                                     : mul2(splat2(-0.33333334f), fma2(ux, Fx, fma2(uy, Fy, mul2(uz, Fz))));
+    // calculate_f_eq, sim.cl:155-207
+    // c3 stays scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false (seen in SASS; the
+    // scalar forms are left alone), which would change the rounding of this sum of squares.  Nowhere else in this function
+    // does a packed product feed a packed ADD (products only enter FMAs, as multiplicand or addend, which cannot be re-fused).
+    const float2 c3 = make_float2(-3.0f * (sq(ux.x) + sq(uy.x) + sq(uz.x)), -3.0f * (sq(ux.y) + sq(uy.y) + sq(uz.y)));
+    const float2 rhom1 = add2(rho, splat2(-1.0f));
+    const float2 u3x = mul2(ux, splat2(3.0f)), u3y = mul2(uy, splat2(3.0f)), u3z = mul2(uz, splat2(3.0f));
+    auto relax = [&](float2 old, float2 feq, float2 Fin) {  // SRT, sim.cl:720 / 653
+        return fma2(W1, old, fma2(W, feq, mul2(Fin, CT)));
+    };
+    {
+        const float2 feq0 = mul2(splat2(wclass<VS>(0)), fma2(rho, mul2(HALF, c3), rhom1));
+        float2 Fin0 = mul2(splat2(9.0f * wclass<VS>(0)), uF);
+        if (!vf) Fin0.x = 0.0f;
+        const float2 o = relax(make_float2(f[0], e[0]), feq0, Fin0);
+        float g = o.x;
+        if (TRT) {  // direction 0 is its own opposite (fhb[0] = fhn[0], feb[0] = feq[0], Fib[0] = Fin[0])
+            float F0 = Fin0.x;
+            if (vf) F0 = fmaf(fmaf(w, -0.25f, 0.5f), F0 + F0, fmaf(wm, -0.25f, 0.5f) * (F0 - F0));
+            g = fmaf(0.5f * w, feq0.x - f[0] + feq0.x - f[0], fmaf(0.5f * wm, feq0.x - feq0.x - f[0] + f[0], f[0] + F0));
+        }
+        f[0] = is_e ? feq0.x : g;
+        e[0] = is_e ? feq0.y : o.y;
+    }
+#pragma unroll
+    for (int i = 1; i < QQ; i += 2) {
+        const float wi = wdir<VS>(i);
+        const float2 cf = cdot2<VS>(i, Fx, Fy, Fz), cu = cdot2<VS>(i, ux, uy, uz);
+        float2 Fa = mul2(splat2(9.0f * wi), fma2(cf, add2(cu, THIRD), uF));
+        float2 Fb = mul2(splat2(9.0f * wi), fma2(neg2(cf), add2(neg2(cu), THIRD), uF));
+        if (!vf) { Fa.x = 0.0f; Fb.x = 0.0f; }
+        const float2 rhow = mul2(splat2(wi), rho), rhom1w = mul2(splat2(wi), rhom1);
+        const float2 ui = cdot2<VS>(i, u3x, u3y, u3z);
+        const float2 t = fma2(ui, ui, c3);
+        const float2 qa = fma2(rhow, fma2(HALF, t, ui), rhom1w);
+        const float2 qb = fma2(rhow, fma2(HALF, t, neg2(ui)), rhom1w);
+        const float2 oa = relax(make_float2(f[i], e[i]), qa, Fa);
+        const float2 ob = relax(make_float2(f[i + 1], e[i + 1]), qb, Fb);
+        float ga = oa.x, gb = ob.x;
+        if (TRT) {
+            ga = f[i];
+            gb = f[i + 1];
+            trt_pair(ga, gb, qa.x, qb.x, Fa.x, Fb.x, w, wm, vf);
+        }
+        f[i] = is_e ? qa.x : ga;
+        f[i + 1] = is_e ? qb.x : gb;
+        e[i] = is_e ? qa.y : oa.y;
+        e[i + 1] = is_e ? qb.y : ob.y;
     }
 }
 

@@ -34,15 +34,27 @@ constexpr int SC_BLOCK_MAX = 256;
 #ifndef ION_SC_MINB
 #define ION_SC_MINB 8
 #endif
+// ION_SC_PACKED = 1: the MHD kernel evaluates the neutral gas and the electron gas together in packed FP32 (lattice.cuh,
+// collide_two_species); 0: the scalar sequence (A/B build switch).  Results are bit-identical either way.
+#ifndef ION_SC_PACKED
+#define ION_SC_PACKED 1
+#endif
 
 struct LodDeposit {
-    uint32_t ind;  // float index of the LOD entry (already *4), 0xFFFFFFFF = nothing to deposit
+    uint32_t ind;  // entry of the own finest LOD level (lod_index of the cell), 0xFFFFFFFF = nothing to deposit
     float q, ux, uy, uz;
 };
 
-// Warp-segmented reduction of LOD deposits: lanes of one warp are consecutive x cells, so equal LOD indices form
-// contiguous runs; each run is summed with shuffles and its head lane issues the 4 reductions.
-__device__ __forceinline__ void lod_deposit_warp(float* __restrict__ QU_lod, LodDeposit d) {
+// LOD deposit (sim.cl:666-677: four float atomics per cell onto the cell's finest-level LOD entry).
+//   1. Lanes of a warp are consecutive x cells, so equal LOD entries form contiguous runs: each run is summed with shuffles and
+//      only its head lane touches memory.
+//   2. Same-address reductions serialise in L2 (~10 ns each, measured: 3.8 ms for the 256^3 kernel at depth 1 against 1.2 ms at
+//      depth 3), and the blocks resident at one time sit in a handful of LOD blocks -- 20 entries at 512^3, 16 at
+//      2048x2048x128 -- so with one copy of the pyramid the deposit alone took 8 ms of the 12.7 ms 512^3 kernel.  The deposit
+//      therefore goes to one of lod_rep_count private replicas of the finest level, picked by block coordinates so that
+//      neighbouring resident blocks use different replicas, as ONE 16-byte vector reduction (red.global.add.v4.f32) per run;
+//      k_lod_fold adds the replicas into QU_lod (and clears them) right after the kernel.
+__device__ __forceinline__ void lod_deposit_warp(const KArgs& a, LodDeposit d, uint32_t own_offset) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const uint32_t prev = __shfl_up_sync(full, d.ind, 1);
@@ -61,21 +73,33 @@ __device__ __forceinline__ void lod_deposit_warp(float* __restrict__ QU_lod, Lod
         }
     }
     if (head && d.ind != 0xFFFFFFFFu) {
-        atomicAdd(&QU_lod[d.ind + 0], d.q);
-        atomicAdd(&QU_lod[d.ind + 1], d.ux);
-        atomicAdd(&QU_lod[d.ind + 2], d.uy);
-        atomicAdd(&QU_lod[d.ind + 3], d.uz);
+        if (d.ind < a.lod_rep_entries) {
+            const uint32_t rep = (blockIdx.x + 7u * blockIdx.y + 13u * blockIdx.z) & a.lod_rep_mask;
+            float* p = a.lod_rep + ((size_t)rep * a.lod_rep_entries + d.ind) * 4u;
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(d.q), "f"(d.ux), "f"(d.uy), "f"(d.uz) : "memory");
+        } else {  // quirk Q7: an index past the own finest level but inside QU_lod is hit like in the reference
+            float* p = a.QU_lod + (size_t)(d.ind + own_offset) * 4u;
+            atomicAdd(p + 0, d.q);
+            atomicAdd(p + 1, d.ux);
+            atomicAdd(p + 2, d.uy);
+            atomicAdd(p + 3, d.uz);
+        }
     }
 }
 
-// Resident blocks per SM the register allocation has to allow.  The MHD kernel keeps 2Q+7+6 loaded values live (128
-// registers, 8 blocks of 64 threads; capping it lower spills and is slower).  The plain kernel has only Q loads per thread in
-// flight, so it needs more warps to cover the HBM latency: measured at 256^3 FP32 (profiles/r1_stream_collide_ab.md) D3Q19
-// reaches 4.87 TB/s at <= 64 registers (16 blocks) against 4.32 TB/s at 128; D3Q27 is best at <= 112 registers (9 blocks).
+// Resident blocks (of 64 threads) per SM the register allocation has to allow, measured per kernel family at 256^3
+// (profiles/r1_stream_collide_ab.md, r1b table): the MHD kernels keep 2Q+7+6 loaded values live -- 128 registers / 8 blocks for
+// FP32 and FP16S (capping lower spills and is slower), 96 registers / 10 blocks for FP16C whose codec needs fewer temporaries.
+// The plain kernels have only Q loads per thread in flight and need more warps to cover the HBM latency: FP32 SRT is best at
+// 80 registers / 12 blocks (0.87 of the copy peak vs 0.83 at 16 blocks, whose 64-register cap spills), TRT and the FP16 codecs
+// at 16 blocks, D3Q27 at 9.
 #ifndef ION_SC_MINB_PLAIN
 #define ION_SC_MINB_PLAIN 16
 #endif
-template <int VS, bool MHD> struct ScMinBlocks { static constexpr int value = MHD ? ION_SC_MINB : (VSet<VS>::Q > 19 ? 9 : ION_SC_MINB_PLAIN); };
+template <int VS, int FP, bool MHD, bool TRT> struct ScMinBlocks {
+    static constexpr int value = MHD ? (FP == ION_FP16C ? 10 : ION_SC_MINB)
+                                     : (VSet<VS>::Q > 19 ? 9 : (FP == ION_FP32 && !TRT ? 12 : ION_SC_MINB_PLAIN));
+};
 
 // SUBGRID_ECR helpers, sim.cl:449-461
 __device__ __forceinline__ float mag_v(const float* __restrict__ V, uint64_t N, uint32_t n) {
@@ -83,44 +107,46 @@ __device__ __forceinline__ float mag_v(const float* __restrict__ V, uint64_t N, 
 }
 __device__ __forceinline__ float length3(float x, float y, float z) { return sqrtf(x * x + y * y + z * z); }  // OpenCL length()
 
-template <int VS, int FP, bool MHD, bool TRT, bool ECR>
-__global__ void __launch_bounds__(ION_SC_BLOCK, ScMinBlocks<VS, MHD>::value)
-k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float fx, const float fy, const float fz) {
+template <int VS, int FP, bool MHD, bool TRT, bool ECR, bool ODD>
+__global__ void __launch_bounds__(ION_SC_BLOCK, ScMinBlocks<VS, FP, MHD, TRT>::value)
+k_stream_collide(const __grid_constant__ KArgs a, const float fx, const float fy, const float fz) {
     constexpr int QQ = VSet<VS>::Q;
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
     const bool inside = x < a.nx && !is_halo(a, x, y, z);  // sim.cl:485
     const Cell c = make_cell(a, inside ? x : 0u, y, z);
     const uint32_t n = c.n;
     const uint64_t N = a.N;
-    const uint64_t todd = t & 1ull;
     auto nb = [&](int i) { return neighbor<VS>(c, i); };
 
     // ---- every load of the cell is issued BEFORE the flag is known (sim.cl:487 returns first): the flag byte would
     // otherwise cost one full HBM round trip during which the warp has nothing in flight.  A solid cell's DDFs are read and
     // dropped (a few % extra reads in scenes with solids, none in the fluid bulk); results are unchanged. ----
-    const uint8_t flagsn = inside ? a.flags[n] : (uint8_t)ION_TYPE_S;
     float fhn[QQ];
-    ep_load<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 2, sim.cl:494
+    ep_load_p<FP, QQ, ODD>(fhn, a.fi, N, n, nb);  // streaming part 2, sim.cl:494
     float ehn[MHD ? QQ : 1];
     float qhn[7];
     float Bx = 0.f, By = 0.f, Bz = 0.f, Ex = 0.f, Ey = 0.f, Ez = 0.f;
     if (MHD) {
-        Bx = a.B_dyn[n]; By = a.B_dyn[N + n]; Bz = a.B_dyn[2ull * N + n];  // sim.cl:532-533
-        Ex = a.E_dyn[n]; Ey = a.E_dyn[N + n]; Ez = a.E_dyn[2ull * N + n];
-        ep_load<FP, QQ>(ehn, a.ei, N, n, todd, nb);                         // sim.cl:538
-        ep_load<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
+        Bx = ld_f32_pinned(a.B_dyn + n); By = ld_f32_pinned(a.B_dyn + N + n); Bz = ld_f32_pinned(a.B_dyn + 2ull * N + n);  // sim.cl:532-533
+        Ex = ld_f32_pinned(a.E_dyn + n); Ey = ld_f32_pinned(a.E_dyn + N + n); Ez = ld_f32_pinned(a.E_dyn + 2ull * N + n);
+        ep_load_p<FP, QQ, ODD>(ehn, a.ei, N, n, nb);                         // sim.cl:538
+        ep_load_p<FP, 7, ODD>(qhn, a.fqi, N, n, [&](int i) { return neighbor7(c, i); });  // sim.cl:550
     }
     float ethn[ECR ? 7 : 1];
     float Evx = 0.f, Evy = 0.f, Evz = 0.f;
     if (ECR) {
-        ep_load<FP, 7>(ethn, a.eti, N, n, todd, [&](int i) { return neighbor7(c, i); });  // sim.cl:566
+        ep_load_p<FP, 7, ODD>(ethn, a.eti, N, n, [&](int i) { return neighbor7(c, i); });  // sim.cl:566
         Evx = a.E_var[n]; Evy = a.E_var[N + n]; Evz = a.E_var[2ull * N + n];                // sim.cl:579
     }
+    // the flag byte is requested LAST: the loads above are pinned (asm volatile), so the branch on the flag cannot be scheduled
+    // in front of them (nvcc otherwise duplicates the loads into both sides of that branch and the warp idles one round trip)
+    const uint8_t flagsn = inside ? ld_u8_pinned(a.flags + n) : (uint8_t)ION_TYPE_S;
     const bool active = (flagsn & ION_TYPE_BO) != ION_TYPE_S;  // sim.cl:487-488 (quirk Q1: only exact TYPE_S is solid)
 
     LodDeposit dep;
     dep.ind = 0xFFFFFFFFu;
     dep.q = dep.ux = dep.uy = dep.uz = 0.0f;
+    uint32_t lod_off = 0u;  // first entry of the own finest level inside QU_lod (multi-domain layout), sim.cl:667-670
     if (!MHD && !active) return;
 
     if (active) {
@@ -130,7 +156,20 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
         const bool is_e = eqb && bo == ION_TYPE_E;
 
         float rhon, uxn, uyn, uzn;
-        if (is_e) {  // sim.cl:503-507
+        float rhon_e = 0.0f, uxn_e = 0.0f, uyn_e = 0.0f, uzn_e = 0.0f;  // electron gas (MHD)
+        float efx = 0.0f, efy = 0.0f, efz = 0.0f;
+        if (MHD && ION_SC_PACKED) {  // gas and electron moments in the two lanes of packed FP32 (sim.cl:496-511,537-540)
+            float2 rho2, m2[3];
+            rho_m2<VS>(fhn, ehn, rho2, m2);
+            rhon = rho2.x; uxn = m2[0].x / rho2.x; uyn = m2[1].x / rho2.x; uzn = VS == ION_D2Q9 ? 0.0f / rho2.x : m2[2].x / rho2.x;
+            rhon_e = rho2.y; uxn_e = m2[0].y / rho2.y; uyn_e = m2[1].y / rho2.y; uzn_e = VS == ION_D2Q9 ? 0.0f / rho2.y : m2[2].y / rho2.y;
+            if (is_e) {
+                rhon = a.rho[n];
+                uxn = a.u[n];
+                uyn = a.u[N + n];
+                uzn = a.u[2ull * N + n];
+            }
+        } else if (is_e) {  // sim.cl:503-507
             rhon = a.rho[n];
             uxn = a.u[n];
             uyn = a.u[N + n];
@@ -151,8 +190,7 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
 
         if (MHD) {
             // electron gas part 1, sim.cl:537-540
-            float rhon_e, uxn_e, uyn_e, uzn_e;
-            rho_u<VS>(ehn, rhon_e, uxn_e, uyn_e, uzn_e);
+            if (!ION_SC_PACKED) rho_u<VS>(ehn, rhon_e, uxn_e, uyn_e, uzn_e);
             // gas charge advection 1, sim.cl:551-553
             float rhon_q = 0.0f;
 #pragma unroll
@@ -190,7 +228,7 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                 const float wq = a.wq;
 #pragma unroll
                 for (int i = 0; i < 7; i++) ethn[i] = fmaf(1.0f - wq, ethn[i], wq * eteq[i]);
-                ep_store<FP, 7>(ethn, a.eti, N, n, todd, [&](int i) { return neighbor7(c, i); });
+                ep_store_p<FP, 7, ODD>(ethn, a.eti, N, n, [&](int i) { return neighbor7(c, i); });
                 // ionization
                 const float delta_q_rho = 0.0001f * Etn;
                 rhon_e += delta_q_rho;
@@ -204,25 +242,27 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                 const float wq = a.wq;
 #pragma unroll
                 for (int i = 0; i < 7; i++) qhn[i] = fmaf(1.0f - wq, qhn[i], wq * qeq[i]);
-                ep_store<FP, 7>(qhn, a.fqi, N, n, todd, [&](int i) { return neighbor7(c, i); });
+                ep_store_p<FP, 7, ODD>(qhn, a.fqi, N, n, [&](int i) { return neighbor7(c, i); });
             }
             // electron gas part 2, sim.cl:641-656
             const float nre = -rhon_e;
-            const float efx = nre * (Ex + (uyn_e * Bz - uzn_e * By));
-            const float efy = nre * (Ey + (uzn_e * Bx - uxn_e * Bz));
-            const float efz = nre * (Ez + (uxn_e * By - uyn_e * Bx));
+            efx = nre * (Ex + (uyn_e * Bz - uzn_e * By));
+            efy = nre * (Ey + (uzn_e * Bx - uxn_e * Bz));
+            efz = nre * (Ez + (uxn_e * By - uyn_e * Bx));
             const float rho2_e = 0.5f / (rhon_e * a.kkge);
             uxn_e = clampf(fmaf(efx, rho2_e, uxn_e), -ION_DEF_C, ION_DEF_C);
             uyn_e = clampf(fmaf(efy, rho2_e, uyn_e), -ION_DEF_C, ION_DEF_C);
             uzn_e = clampf(fmaf(efz, rho2_e, uzn_e), -ION_DEF_C, ION_DEF_C);
-            forcing_terms<VS>(uxn_e, uyn_e, uzn_e, efx, efy, efz, Fin);
-            f_eq<VS>(rhon_e, uxn_e, uyn_e, uzn_e, feq);
+            if (!ION_SC_PACKED) {  // scalar electron relaxation; the packed build relaxes both species together below
+                forcing_terms<VS>(uxn_e, uyn_e, uzn_e, efx, efy, efz, Fin);
+                f_eq<VS>(rhon_e, uxn_e, uyn_e, uzn_e, feq);
 #pragma unroll
-            for (int i = 0; i < QQ; i++) {
-                const float Fi = Fin[i] * c_tau;
-                ehn[i] = is_e ? feq[i] : fmaf(1.0f - w, ehn[i], fmaf(w, feq[i], Fi));  // always SRT, sim.cl:649-655
+                for (int i = 0; i < QQ; i++) {
+                    const float Fi = Fin[i] * c_tau;
+                    ehn[i] = is_e ? feq[i] : fmaf(1.0f - w, ehn[i], fmaf(w, feq[i], Fi));  // always SRT, sim.cl:649-655
+                }
+                ep_store_p<FP, QQ, ODD>(ehn, a.ei, N, n, nb);
             }
-            ep_store<FP, QQ>(ehn, a.ei, N, n, todd, nb);
             // EM force on gas (pre-force gas velocity), sim.cl:660-662
             fxn += rhon_q * (Ex + uyn * Bz - uzn * By);
             fyn += rhon_q * (Ey + uzn * Bx - uxn * Bz);
@@ -236,8 +276,9 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                 // quirk Q7: on split axes the halo-inclusive division can point past the own finest level; entries
                 // inside the buffer are hit like in the reference, a deposit past DEF_NUM_LOD (undefined behaviour
                 // there) is dropped
-                const uint32_t li = lod_index(a, x, y, z, a.lod_depth) + off;
-                dep.ind = li < a.n_lod ? li * 4u : 0xFFFFFFFFu;
+                const uint32_t lc = lod_index(a, x, y, z, a.lod_depth);
+                dep.ind = lc + off < a.n_lod ? lc : 0xFFFFFFFFu;
+                lod_off = off;
                 const float ils = 1.0f / lod_s(a, a.lod_depth);
                 dep.q = rhon_q - rhon_e;
                 dep.ux = uxn * ils;
@@ -246,18 +287,21 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
             }
         }
 
+        constexpr bool PACKED = MHD && ION_SC_PACKED;
         if (vf) {  // sim.cl:680-685
             const float rho2 = 0.5f / rhon;
             uxn = clampf(fmaf(fxn, rho2, uxn), -ION_DEF_C, ION_DEF_C);
             uyn = clampf(fmaf(fyn, rho2, uyn), -ION_DEF_C, ION_DEF_C);
             uzn = clampf(fmaf(fzn, rho2, uzn), -ION_DEF_C, ION_DEF_C);
-            forcing_terms<VS>(uxn, uyn, uzn, fxn, fyn, fzn, Fin);
+            if (!PACKED) forcing_terms<VS>(uxn, uyn, uzn, fxn, fyn, fzn, Fin);
         } else {  // sim.cl:687-690
             uxn = clampf(uxn, -ION_DEF_C, ION_DEF_C);
             uyn = clampf(uyn, -ION_DEF_C, ION_DEF_C);
             uzn = clampf(uzn, -ION_DEF_C, ION_DEF_C);
+            if (!PACKED) {
 #pragma unroll
-            for (int i = 0; i < QQ; i++) Fin[i] = 0.0f;
+                for (int i = 0; i < QQ; i++) Fin[i] = 0.0f;
+            }
         }
 
         if ((a.ext & ION_EXT_UPDATE_FIELDS) && !is_e) {  // sim.cl:694-710
@@ -267,6 +311,12 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
             a.u[2ull * N + n] = uzn;
         }
 
+        if (PACKED) {  // equilibrium, forcing and relaxation of gas + electrons, two lanes (sim.cl:641-656,712-755)
+            collide_two_species<VS, TRT>(fhn, ehn, make_float2(rhon, rhon_e), make_float2(uxn, uxn_e), make_float2(uyn, uyn_e),
+                                         make_float2(uzn, uzn_e), make_float2(fxn, efx), make_float2(fyn, efy), make_float2(fzn, efz), w, true /* MHD implies VOLUME_FORCE, checked at create */, is_e);
+            ep_store_p<FP, QQ, ODD>(ehn, a.ei, N, n, nb);
+            ep_store_p<FP, QQ, ODD>(fhn, a.fi, N, n, nb);  // streaming part 1, sim.cl:757
+        } else {
         f_eq<VS>(rhon, uxn, uyn, uzn, feq);  // sim.cl:712
 
         if (!TRT) {  // sim.cl:714-723
@@ -307,7 +357,8 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                                      fmaf(0.5f * wm, feq[i] - feb[i] - fhn[i] + fhb[i], fhn[i] + Fin[i]));
             }
         }
-        ep_store<FP, QQ>(fhn, a.fi, N, n, todd, nb);  // streaming part 1, sim.cl:757
+        ep_store_p<FP, QQ, ODD>(fhn, a.fi, N, n, nb);  // streaming part 1, sim.cl:757
+        }
     }
 
     if (MHD) {
@@ -318,7 +369,7 @@ k_stream_collide(const __grid_constant__ KArgs a, const uint64_t t, const float 
                 a.lod_u[2ull * a.N + n] = dep.uz;
             }
         } else {
-            lod_deposit_warp(a.QU_lod, dep);
+            lod_deposit_warp(a, dep, lod_off);
         }
     }
 }
@@ -409,10 +460,11 @@ cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt,
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
 
-#define ION_SC_CASE(FPV, MHDV, TRTV, ECRV)                                                             \
-    if (fp == FPV && mhd == MHDV && trt == TRTV && ecr == ECRV) {                                      \
-        k_stream_collide<VS, FPV, MHDV, TRTV, ECRV><<<grid, block, 0, s>>>(a, t, fx, fy, fz);          \
-        return cudaGetLastError();                                                                     \
+#define ION_SC_CASE(FPV, MHDV, TRTV, ECRV)                                                                 \
+    if (fp == FPV && mhd == MHDV && trt == TRTV && ecr == ECRV) {                                          \
+        if (t & 1ull) k_stream_collide<VS, FPV, MHDV, TRTV, ECRV, true><<<grid, block, 0, s>>>(a, fx, fy, fz);  \
+        else k_stream_collide<VS, FPV, MHDV, TRTV, ECRV, false><<<grid, block, 0, s>>>(a, fx, fy, fz);         \
+        return cudaGetLastError();                                                                         \
     }
 
 #define ION_DEFINE_VS_LAUNCHERS(VSV, ALLOW_MHD)                                                                      \

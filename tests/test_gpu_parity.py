@@ -88,6 +88,13 @@ def test_codecs_exhaustive(gpu_lib):
                  np.float32),
         (codes.astype(np.float32) / 2048.0 * np.float32(2.0 ** -14)).astype(np.float32),  # FP16C denormal grid incl. ties
     ])
+    # FP16C's encoder is a single round-toward-zero multiplication on the device (lattice.cuh): sweep the bit patterns of the
+    # binades around its normal/denormal boundary (2^-28 .. 2^-11), every pattern at the top of each binade (mantissa carries)
+    # and around the 4-bit exponent wrap, both signs
+    sweep = np.arange(0x31000000, 0x3A000000, 29, dtype=np.uint32)
+    tops = np.concatenate([np.arange((e << 23) - 0x1800, (e << 23) + 0x1800, dtype=np.uint32) for e in range(98, 132)])
+    bits = np.concatenate([sweep, tops, np.array([0x7F800000, 0x7F7FFFFF, 0x00000001, 0x007FFFFF, 0x00800000], np.uint32)])
+    x = np.concatenate([x, bits.view(np.float32), (bits | np.uint32(0x80000000)).view(np.float32)])
     for ft, name in ((0, "FP16S"), (1, "FP16C")):
         cfg = rh.RefConfig(velocity_set="D3Q19", float_type=name, n_x=4, n_y=4, n_z=4)
         dom = rh.RefLbm(cfg, threads=1, backend="port").domains[0]

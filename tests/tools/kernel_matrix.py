@@ -21,6 +21,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--side", type=int, default=256)
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--shapes", default="", help="extra D3Q19 FP32 MHD rows, e.g. 512x256x256,512x256x254")
+    ap.add_argument("--lod-depth", type=int, default=3, help="mhd_lod_depth of the MHD rows (LOD deposit atomics)")
+    ap.add_argument("--only", default="", help="run only the rows whose label contains this text (for ncu captures)")
     args = ap.parse_args()
     import torch
     from ionsolver_b200 import lbm as L
@@ -42,9 +45,15 @@ def main():
         ("cfg4 kernel D3Q27 FP16S MHD", dict(velocity_set=V.D3Q27, float_type=F.FP16S, n_x=n, n_y=n, n_z=n, mhd=True)),
         ("cfg5 kernel D3Q19 FP16C MHD", dict(velocity_set=V.D3Q19, float_type=F.FP16C, n_x=n, n_y=n, n_z=n, mhd=True)),
     ]
+    for shp in [x for x in args.shapes.split(",") if x]:
+        sx, sy, sz = (int(v) for v in shp.split("x"))
+        rows.append((f"shape {shp} D3Q19 FP32 MHD", dict(velocity_set=V.D3Q19, float_type=F.FP32, n_x=sx, n_y=sy, n_z=sz, mhd=True)))
+        rows.append((f"shape {shp} D3Q19 FP32 SRT", dict(velocity_set=V.D3Q19, float_type=F.FP32, n_x=sx, n_y=sy, n_z=sz)))
     for label, kw in rows:
+        if args.only and args.only not in label:
+            continue
         mhd = kw.pop("mhd", False)
-        cfg = L.LbmConfig(nu=0.1, graphics_config=L.GraphicsConfig(False), ext_volume_force=mhd, ext_magneto_hydro=mhd, mhd_lod_depth=3, **kw)
+        cfg = L.LbmConfig(nu=0.1, graphics_config=L.GraphicsConfig(False), ext_volume_force=mhd, ext_magneto_hydro=mhd, mhd_lod_depth=args.lod_depth, **kw)
         if mhd:
             cfg.units.set(float(n), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 1e-10, 1.0)
         lbm = L.Lbm(cfg, devices=[0])
