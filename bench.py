@@ -252,6 +252,10 @@ def run_ours(args, rank, world, local_rank):
             kern_ms["clear_qu_lod"] += e[0].elapsed_time(e[1]) / k_prof
             kern_ms["stream_collide"] += e[1].elapsed_time(e[2]) / k_prof
             kern_ms["update_e_b_dynamic"] += e[2].elapsed_time(e[3]) / k_prof
+    if dist is not None:  # slabs differ in how many foreign LOD sources they sum over: report the slowest rank's kernels
+        tk = torch.tensor([kern_ms[k] for k in sorted(kern_ms)], device=f"cuda:{device}", dtype=torch.float64)
+        dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+        kern_ms = {k: float(v) for k, v in zip(sorted(kern_ms), tk.tolist())}
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
     sc_bytes = 1 + 4 * 19 * 4 + 14 * 4 + 24 + 4   # 389 B/cell: MHD stream_collide, D3Q19 FP32
@@ -273,26 +277,34 @@ def run_ours(args, rank, world, local_rank):
                                    "pairs_per_s": pairs / (kern_ms["update_e_b_dynamic"] * 1e-3), "achieved_tflops": eb_tflops,
                                    "fp32_peak_tflops": 2 * fma_peak / 1e12, "fp32_peak_tflops_packed": 2 * fma_peak_packed / 1e12,
                                    "frac_of_fp32_peak": eb_tflops / (2 * fma_peak / 1e12),
-                                   "share_of_step": kern_ms["update_e_b_dynamic"] / ms_step},
+                                   "share_of_step": kern_ms["update_e_b_dynamic"] / ms_step,
+                                   "pairs_note": "pairs = cells x 8^depth, the reference's loop count (sim.cl:943); LOD rows whose entries "
+                                                 "are all zero are skipped by the kernel (in a single-domain run 585 of the 4096 window slots "
+                                                 "are never filled, quirk Q5), so the executed FMA rate is ~14 % below achieved_tflops there"},
             "clear_qu_lod": {"ms": kern_ms["clear_qu_lod"], "share_of_step": kern_ms["clear_qu_lod"] / ms_step},
         }
         # The roofline object is for the dominant kernel of the step.  When that is update_e_b_dynamic (LOD depth 4) the HBM
         # fraction is tiny by construction -- the kernel is bound by CUDA-core FP32 issue, neither by HBM nor by tensor cores
         #  -- so its FP32 roofline is attached under "compute", and stream_collide's HBM roofline under "hbm_kernel".
         dom_name = max(("stream_collide", "update_e_b_dynamic"), key=lambda k: kernels[k]["ms"])
-        dk = kernels[dom_name]
-        roofline = {"kernel": dom_name, "bound": "hbm", "achieved": dk["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
-                    "frac": dk["achieved_gbs"] / hbm_peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})",
-                    "algorithmic_bytes_per_launch": cells_local * dk["bytes_per_cell"], "ms_per_launch": dk["ms"],
-                    "hbm_kernel": {"kernel": "stream_collide", "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak,
-                                   "algorithmic_bytes_per_launch": cells_local * sc_bytes, "ms_per_launch": kern_ms["stream_collide"],
-                                   "traffic": 6.47e9 if args.lod_depth in (3, 4) else None,
-                                   "traffic_source": "profiles/r1_ncu_stream_collide.md: dram__bytes_read.sum + dram__bytes_write.sum"}}
+        hbm_kernel = {"kernel": "stream_collide", "bound": "hbm", "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak,
+                      "algorithmic_bytes_per_launch": cells_local * sc_bytes, "ms_per_launch": kern_ms["stream_collide"],
+                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": 6.477e9,
+                      "traffic_source": "profiles/r1_ncu_stream_collide.md (ncu --set full): dram__bytes_read.sum 3.442 GB + dram__bytes_write.sum 3.035 GB per launch"}
         if dom_name == "update_e_b_dynamic":
-            roofline["compute"] = {"bound": "fp32 (CUDA-core FMA issue)", "achieved": eb_tflops, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
-                                   "frac": eb_tflops / (2 * fma_peak / 1e12), "flop_per_launch": pairs * 18,
-                                   "peak_source": "ion_measure_fma_peak: scalar FFMA micro-benchmark run in this process"}
-            roofline["note"] = "dominant kernel is FP32-issue bound; see 'compute' for its roofline and 'hbm_kernel' for stream_collide"
+            # The dominant kernel of the step at this LOD depth is bound by CUDA-core FP32 issue -- neither by HBM (49 B per cell
+            # against 8^depth x 18 flop) nor by tensor cores -- so its roofline is stated in FP32 TFLOP/s against
+            # the FFMA issue peak measured in this process; the HBM-bound kernel of the step follows under "hbm_kernel".
+            roofline = {"kernel": dom_name, "bound": "fp32", "achieved": eb_tflops, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
+                        "frac": eb_tflops / (2 * fma_peak / 1e12), "flop_per_launch": pairs * 18, "ms_per_launch": kern_ms["update_e_b_dynamic"],
+                        "peak_source": "scalar FFMA issue micro-benchmark run in this process on this GPU (ion_measure_fma_peak); "
+                                       "MEASURED_PEAKS.json has no FP32 entry",
+                        "traffic": 0.792e9, "traffic_source": "profiles/r1_ncu_update_e_b_pair.md: dram__bytes_read.sum + dram__bytes_write.sum",
+                        "hbm_view": {"algorithmic_bytes_per_launch": cells_local * eb_bytes, "achieved_gbs": eb_gbs, "frac_of_hbm_peak": eb_gbs / hbm_peak},
+                        "hbm_kernel": hbm_kernel,
+                        "note": "bound is 'fp32' (CUDA cores), outside the hbm|tensor pair: see DESIGN.md 4.2 for why; 'hbm_kernel' is stream_collide"}
+        else:
+            roofline = dict(hbm_kernel)
 
     # ---- end to end through the public API with HOST buffers: load state -> initialize -> step -> save state ----
     e2e = None

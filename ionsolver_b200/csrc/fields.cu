@@ -733,26 +733,39 @@ cudaError_t launch_lod_deposit_ordered(const KArgs& a, cudaStream_t s) {
 }
 
 // Folds the private replicas of the finest LOD level (stream_collide.cuh, lod_deposit_warp) into QU_lod and clears them for
-// the next step.  One thread per (entry, component): 8^depth * 4 threads, lod_rep_count coalesced reads each.
-__global__ void k_lod_fold(const __grid_constant__ KArgs a, uint32_t own_offset) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t words = a.lod_rep_entries * 4u;
-    if (t >= words) return;
-    float s = 0.0f;
-    for (uint32_t r = 0; r <= a.lod_rep_mask; r++) {
-        float* p = a.lod_rep + (size_t)r * words + t;
-        s += *p;
-        *p = 0.0f;
+// the next step.  One warp per LOD entry: lane r reads (and zeroes) the entry's float4 in replica r, a shuffle tree adds the
+// lanes, lane 0 adds the sum to QU_lod.  (A thread looping over the replicas took 31 us; this is one load per thread.)
+__global__ void __launch_bounds__(256) k_lod_fold(const __grid_constant__ KArgs a, uint32_t own_offset) {
+    const uint32_t entry = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31u;
+    if (entry >= a.lod_rep_entries) return;  // whole warps leave together (blockDim is a multiple of 32)
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (uint32_t r = lane; r <= a.lod_rep_mask; r += 32u) {
+        float4* p = reinterpret_cast<float4*>(a.lod_rep) + (size_t)r * a.lod_rep_entries + entry;
+        const float4 v = *p;
+        *p = make_float4(0.f, 0.f, 0.f, 0.f);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-    const uint32_t entry = (t >> 2) + own_offset;
-    if (entry < a.n_lod) a.QU_lod[(size_t)entry * 4u + (t & 3u)] += s;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        s.x += __shfl_down_sync(0xffffffffu, s.x, off);
+        s.y += __shfl_down_sync(0xffffffffu, s.y, off);
+        s.z += __shfl_down_sync(0xffffffffu, s.z, off);
+        s.w += __shfl_down_sync(0xffffffffu, s.w, off);
+    }
+    const uint32_t e = entry + own_offset;
+    if (lane == 0u && e < a.n_lod) {
+        float4* q = reinterpret_cast<float4*>(a.QU_lod) + e;
+        float4 v = *q;
+        v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w;
+        *q = v;
+    }
 }
 cudaError_t launch_lod_fold(const KArgs& a, cudaStream_t s) {
     uint32_t off = 0u;
     if (a.dx > 1u || a.dy > 1u || a.dz > 1u)
         for (uint32_t d = 0u; d < a.lod_depth; d++) off += 1u << (d * 3u);  // sim.cl:667-670 (to_d of the 3-D sets)
-    const uint32_t words = a.lod_rep_entries * 4u;
-    k_lod_fold<<<(words + 127u) / 128u, 128, 0, s>>>(a, off);
+    const uint64_t threads = (uint64_t)a.lod_rep_entries * 32u;
+    k_lod_fold<<<(unsigned)((threads + 255u) / 256u), 256, 0, s>>>(a, off);
     return cudaGetLastError();
 }
 
