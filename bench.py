@@ -351,6 +351,22 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": mlups, "unit": "MLUPs/s", "cores": cores, "kind": kind, "ms_per_step": ms,
                "sample": f"{SAMPLE_SIDE}^3 lattice of the same scene (same kernels, LOD depth {args.lod_depth}), 2 timed full time steps after 1 warm-up"}
 
+    # Source terms per cell that update_e_b_dynamic sums (sim.cl:940-983).  They GROW with the number of domains -- the own window
+    # is fully populated only in multi-domain runs (quirk Q5 leaves 585 of its 4096 slots empty in a single domain, and all-zero
+    # rows are skipped) and every other slab adds its pyramid level max(depth - distance, 0) -- so MLUPs/s per GPU falls with N at
+    # constant work per SOURCE TERM; this is the reference's algorithm, not communication (halos and LODs overlap with the update).
+    D = args.lod_depth
+    own_fine = 8 ** D
+    if world == 1:
+        empty = sum(8 ** i for i in range(D))
+        terms = {"own": own_fine - (empty // (2 ** D)) * (2 ** D), "foreign_max": 0}
+    else:
+        terms = {"own": own_fine, "foreign_max": max(sum(8 ** max(D - abs(r - o), 0) for o in range(world) if o != r) for r in range(world))}
+    terms["per_cell_slowest_rank"] = terms["own"] + terms["foreign_max"]
+    terms["note"] = ("update_e_b_dynamic work per cell depends on the domain count (reference algorithm: LOD window quirk Q5 + foreign pyramids); "
+                     "compare runs by source terms per second, not only by MLUPs/s")
+    terms["source_terms_per_s_per_gpu"] = terms["per_cell_slowest_rank"] * cells_local / (kern_ms["update_e_b_dynamic"] * 1e-3)
+
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     os.close(saved_stdout)
@@ -359,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "MLUPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "kernels": kernels, "cpu_baseline": cpu,
+            "kernels": kernels, "lod_source_terms": terms, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     lbm.close()
