@@ -144,6 +144,13 @@ ION_API int ion_buffer_device_ptr(const ion_domain_t* dom, int field, void** dpt
 ION_API int ion_buffer_copy(ion_domain_t* dst, int dst_field, size_t dst_offset_bytes, ion_domain_t* src, int src_field,
                     size_t src_offset_bytes, size_t bytes);
 
+/* Slice read-back: the values of one lattice plane of this domain, gathered on the device and copied to host_out.
+ * The reference only DRAWS slices (graphics_field_slice, graphics_kernels.cl:669-706, selected by GraphicsConfig::slice_mode /
+ * slice_x/y/z, graphics.rs:124-130); this is the data half of that view, in the same cell enumeration:
+ * direction 0: a -> (index, a % ny, a / ny); 1: (a / nz, index, a % nz); 2: (a % nx, a / nx, index); halo layers included.
+ * field: RHO, Q, ET (scalars), FLAGS (as float), U, F, E_STAT, B_STAT, E_DYN, B_DYN, E_VAR (component 0,1,2 or 3 = length()). */
+ION_API int ion_read_slice(ion_domain_t* dom, int field, int component, uint32_t direction, uint32_t index, float* host_out);
+
 /* kernels: one per enqueue site ---------------------------------------------------------------------------- */
 ION_API int ion_enqueue_initialize(ion_domain_t* dom);                                          /* domain.rs:412-416 (ends with finish) */
 ION_API int ion_enqueue_stream_collide(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz); /* domain.rs:419-428 */

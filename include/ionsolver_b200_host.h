@@ -105,6 +105,16 @@ ION_API int ion_lbm_read_file(const char* path, IonLbmConfig* cfg_inout, ion_lbm
 ION_API int ion_config_to_json(const IonLbmConfig* cfg, char** json);                                  /* file.rs:323 */
 ION_API int ion_config_from_json(const char* json, IonLbmConfig* cfg);                                 /* file.rs:310 */
 ION_API int ion_lbm_dump_cell(ion_lbm_t* lbm, uint32_t local_index, uint64_t cell, char** text);      /* domain.rs:584 */
+/* Slice read-back and PNG (graphics.rs:124-130 slice_mode / slice_x,y,z, :328-373 PNG frames).  slice_mode 1,2,3 = X,Y,Z
+ * (SliceMode), index = global cell coordinate on that axis, field / component as ion_read_slice.  The plane is assembled over the
+ * local domains without halo layers: X -> out[gy + gz*Ny], Y -> out[gx + gz*Nx], Z -> out[gx + gy*Nx]; capacity in floats. */
+ION_API int ion_lbm_read_slice(ion_lbm_t* lbm, int field, int component, uint32_t slice_mode, uint32_t index, float* out, size_t capacity,
+                               uint32_t* width, uint32_t* height);
+/* one pixel per cell, colour = iron_colormap((value - v_min) / (v_max - v_min)) (graphics_kernels.cl:412-428), second axis up */
+ION_API int ion_lbm_write_slice_png(ion_lbm_t* lbm, int field, int component, uint32_t slice_mode, uint32_t index, float v_min, float v_max,
+                                    const char* path);
+ION_API uint32_t ion_iron_colormap(float x);                                              /* 0xRRGGBB; no GPU needed */
+ION_API int ion_write_png_rgb(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height); /* no GPU needed */
 ION_API void ion_free(void* p);
 
 #ifdef __cplusplus

@@ -47,7 +47,7 @@ SYMBOLS = [
     "ion_kernel_launch_count", "ion_domain_stream",
     "ion_exchange_transfer", "ion_copy_lods", "ion_comm_unique_id", "ion_comm_create", "ion_comm_destroy",
     "ion_comm_exchange_transfer", "ion_comm_exchange_lods", "ion_neighbor_domains", "ion_lod_exchange_plan",
-    "ion_measure_fma_peak", "ion_halo_fork", "ion_halo_join", "ion_codec_probe",
+    "ion_measure_fma_peak", "ion_halo_fork", "ion_halo_join", "ion_codec_probe", "ion_read_slice",
 ]
 # every symbol include/ionsolver_b200_host.h declares
 HOST_SYMBOLS = [
@@ -59,7 +59,8 @@ HOST_SYMBOLS = [
     "ion_lbm_voxelise_mesh", "ion_lbm_mesh_info", "ion_lbm_mesh_triangles", "ion_lbm_mesh_translate",
     "ion_lbm_set_taylor_green", "ion_lbm_setup_velocity_field", "ion_setup_taylor_green", "ion_setup_lid_driven_cavity",
     "ion_setup_charged_fluid", "ion_lbm_encode", "ion_lbm_decode", "ion_lbm_write_file", "ion_lbm_read_file",
-    "ion_config_to_json", "ion_config_from_json", "ion_lbm_dump_cell", "ion_free",
+    "ion_config_to_json", "ion_config_from_json", "ion_lbm_dump_cell", "ion_lbm_read_slice", "ion_lbm_write_slice_png",
+    "ion_iron_colormap", "ion_write_png_rgb", "ion_free",
 ]
 COMM_ID_BYTES = 128
 
@@ -206,6 +207,12 @@ def load() -> ctypes.CDLL:
     L.ion_config_to_json.argtypes = [CFG, c.POINTER(c.c_void_p)]
     L.ion_config_from_json.argtypes = [c.c_char_p, CFG]
     L.ion_lbm_dump_cell.argtypes = [H, c.c_uint32, c.c_uint64, c.POINTER(c.c_void_p)]
+    L.ion_lbm_read_slice.argtypes = [H, c.c_int, c.c_int, c.c_uint32, c.c_uint32, c.c_void_p, c.c_size_t, c.POINTER(c.c_uint32), c.POINTER(c.c_uint32)]
+    L.ion_lbm_write_slice_png.argtypes = [H, c.c_int, c.c_int, c.c_uint32, c.c_uint32, c.c_float, c.c_float, c.c_char_p]
+    L.ion_iron_colormap.argtypes = [c.c_float]
+    L.ion_iron_colormap.restype = c.c_uint32
+    L.ion_write_png_rgb.argtypes = [c.c_char_p, c.c_void_p, c.c_uint32, c.c_uint32]
+    L.ion_read_slice.argtypes = [D, c.c_int, c.c_int, c.c_uint32, c.c_uint32, c.c_void_p]
     L.ion_free.argtypes = [c.c_void_p]
     L.ion_free.restype = None
     _lib = L

@@ -422,6 +422,59 @@ int ion_buffer_copy(ion_domain_t* dst, int df, size_t doff, ion_domain_t* src, i
     return ION_OK;
 }
 
+// ---- slice read-back: the data half of the reference's slice view (graphics_kernels.cl:669-706 enumerates the cells of a
+// slice as a -> (slice_x, a%NY, a/NY) | (a/NZ, slice_y, a%NZ) | (a%NX, a/NX, slice_z); component 3 = length(), :689) ----
+__global__ void k_gather_slice(const void* __restrict__ buf, int is_u8, int planes, uint64_t N, uint32_t nx, uint32_t ny, uint32_t nz,
+                               int component, uint32_t direction, uint32_t index, float* __restrict__ out, uint32_t area) {
+    const uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= area) return;
+    uint32_t x, y, z;
+    if (direction == 0u) { x = index; y = a % ny; z = a / ny; }
+    else if (direction == 1u) { x = a / nz; y = index; z = a % nz; }
+    else { x = a % nx; y = a / nx; z = index; }
+    const uint64_t n = (uint64_t)x + ((uint64_t)y + (uint64_t)z * ny) * nx;
+    float v;
+    if (is_u8) v = (float)reinterpret_cast<const uint8_t*>(buf)[n];
+    else {
+        const float* f = reinterpret_cast<const float*>(buf);
+        if (planes == 1) v = f[n];
+        else if (component < 3) v = f[(uint64_t)component * N + n];
+        else v = sqrtf(sq(f[n]) + sq(f[N + n]) + sq(f[2ull * N + n]));
+    }
+    out[a] = v;
+}
+
+int ion_read_slice(ion_domain_t* d, int field, int component, uint32_t direction, uint32_t index, float* host_out) {
+    int r = check_field(d, field);
+    if (r) return r;
+    if (!host_out) return fail(ION_ERR_INVALID, "NULL host pointer");
+    int planes = 0, is_u8 = 0;
+    switch (field) {
+        case ION_FIELD_RHO: case ION_FIELD_Q: case ION_FIELD_ET: planes = 1; break;
+        case ION_FIELD_U: case ION_FIELD_F: case ION_FIELD_E_STAT: case ION_FIELD_B_STAT: case ION_FIELD_E_DYN: case ION_FIELD_B_DYN:
+        case ION_FIELD_E_VAR: planes = 3; break;
+        case ION_FIELD_FLAGS: planes = 1; is_u8 = 1; break;
+        default: return fail(ION_ERR_UNSUPPORTED, "field %d is not a per-cell scalar / vector / flag field", field);
+    }
+    const IonParams& p = d->params;
+    if (direction > 2u) return fail(ION_ERR_INVALID, "slice direction %u (0,1,2 = x,y,z)", direction);
+    if (planes == 3 && (component < 0 || component > 3)) return fail(ION_ERR_INVALID, "vector component %d (0,1,2 or 3 = magnitude)", component);
+    const uint32_t extent = direction == 0u ? p.nx : direction == 1u ? p.ny : p.nz;
+    if (index >= extent) return fail(ION_ERR_RANGE, "slice index %u outside the domain (%u cells)", index, extent);
+    const uint32_t area = direction == 0u ? p.ny * p.nz : direction == 1u ? p.nx * p.nz : p.nx * p.ny;
+    ION_CUDA(cudaSetDevice(d->device));
+    float* tmp = nullptr;
+    ION_CUDA(cudaMalloc((void**)&tmp, (size_t)area * sizeof(float)));
+    k_gather_slice<<<(area + 255u) / 256u, 256, 0, d->stream>>>(d->buf[field], is_u8, planes, d->k.N, p.nx, p.ny, p.nz, component, direction, index, tmp, area);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out, tmp, (size_t)area * sizeof(float), cudaMemcpyDeviceToHost, d->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) return cuda_fail(e, "read_slice");
+    return ION_OK;
+}
+
 #define ION_VS_DISPATCH(fn, ...)                                                 \
     switch (d->params.velocity_set) {                                            \
         case ION_D2Q9: e = fn<ION_D2Q9>(__VA_ARGS__); break;                     \

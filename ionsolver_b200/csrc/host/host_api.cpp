@@ -1,7 +1,9 @@
 // host_api.cpp -- extern "C" face of the host layer (include/ionsolver_b200_host.h).  Exceptions of the C++ host
 // become status codes + ion_last_error_string(), exactly like the device ABI.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 
 #include "../../../include/ionsolver_b200_host.h"
 #include "lbm.hpp"
@@ -299,6 +301,35 @@ int ion_lbm_dump_cell(ion_lbm_t* l, uint32_t local_index, uint64_t cell, char** 
     ION_NEED(l);
     if (!text || local_index >= l->lbm->domains.size() || cell >= l->lbm->domains[local_index].n) return ion::fail(ION_ERR_INVALID, "bad dump_cell query");
     ION_TRY(*text = dup_string(l->lbm->domains[local_index].dump_cell(cell)))
+}
+int ion_lbm_read_slice(ion_lbm_t* l, int field, int component, uint32_t slice_mode, uint32_t index, float* out, size_t capacity,
+                       uint32_t* width, uint32_t* height) {
+    ION_NEED(l);
+    if (!out || !width || !height) return ion::fail(ION_ERR_INVALID, "NULL argument");
+    ION_TRY({
+        std::vector<float> plane;
+        slice::read(*l->lbm, field, component, slice_mode, index, plane, *width, *height);
+        if (plane.size() > capacity) throw IonException(ION_ERR_RANGE, "slice needs " + std::to_string(plane.size()) + " floats");
+        memcpy(out, plane.data(), plane.size() * sizeof(float));
+    })
+}
+int ion_lbm_write_slice_png(ion_lbm_t* l, int field, int component, uint32_t slice_mode, uint32_t index, float v_min, float v_max,
+                            const char* path) {
+    ION_NEED(l);
+    if (!path) return ion::fail(ION_ERR_INVALID, "NULL path");
+    ION_TRY(slice::write_png(*l->lbm, field, component, slice_mode, index, v_min, v_max, path))
+}
+uint32_t ion_iron_colormap(float x) { return slice::iron_colormap(x); }
+int ion_write_png_rgb(const char* path, const uint8_t* rgb, uint32_t width, uint32_t height) {
+    if (!path || !rgb) return ion::fail(ION_ERR_INVALID, "NULL argument");
+    ION_TRY({
+        const std::vector<uint8_t> png = slice::encode_png_rgb(rgb, width, height);
+        FILE* f = fopen(path, "wb");
+        if (!f) throw IonException(ION_ERR_INVALID, std::string("cannot open \"") + path + "\" for writing");
+        const size_t n = fwrite(png.data(), 1, png.size(), f);
+        fclose(f);
+        if (n != png.size()) throw IonException(ION_ERR_INVALID, "short write");
+    })
 }
 void ion_free(void* p) { free(p); }
 

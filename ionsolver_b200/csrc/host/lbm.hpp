@@ -250,4 +250,12 @@ LbmConfig read_config(const std::string& path);
 std::vector<uint8_t> read_file(const std::string& path);
 }  // namespace file
 
+// ---- slice read-back + PNG (slice.cpp; graphics.rs:124-130 slice selection, :328-373 PNG frames) --------------------
+namespace slice {
+void read(Lbm& lbm, int field, int component, uint32_t slice_mode, uint32_t index, std::vector<float>& out, uint32_t& w, uint32_t& h);
+void write_png(Lbm& lbm, int field, int component, uint32_t slice_mode, uint32_t index, float v_min, float v_max, const std::string& path);
+uint32_t iron_colormap(float x);                                                   // graphics_kernels.cl:412-428 -> 0xRRGGBB
+std::vector<uint8_t> encode_png_rgb(const uint8_t* rgb, uint32_t w, uint32_t h);   // 8-bit RGB, stored deflate blocks
+}  // namespace slice
+
 }  // namespace ionhost

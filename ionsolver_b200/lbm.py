@@ -365,6 +365,24 @@ class Lbm:
         check(capi.load().ion_lbm_read_file(str(path).encode(), c, ctypes.byref(h)))
         return cls(_handle=h)
 
+    def read_slice(self, field, slice_mode, index, component=3):
+        """One plane of a field over the whole lattice, halo layers removed (SliceMode 1,2,3 = X,Y,Z of graphics.rs:124-130;
+        component 0,1,2 or 3 = magnitude for vector fields).  Returns a float32 array [height, width]:
+        X -> [z, y], Y -> [z, x], Z -> [y, x]."""
+        cfg = self.config
+        w = cfg.n_y if slice_mode == 1 else cfg.n_x
+        h = cfg.n_y if slice_mode == 3 else cfg.n_z
+        out = np.empty(w * h, np.float32)
+        cw, ch = ctypes.c_uint32(), ctypes.c_uint32()
+        check(self.lib.ion_lbm_read_slice(self.handle, int(field), int(component), int(slice_mode), int(index), out.ctypes.data, out.size,
+                                          ctypes.byref(cw), ctypes.byref(ch)))
+        return out.reshape(ch.value, cw.value)
+
+    def write_slice_png(self, path, field, slice_mode, index, v_min=0.0, v_max=1.0, component=3):
+        """Colour-mapped slice as an RGB PNG, one pixel per cell (the reference saves rendered frames, graphics.rs:328-373)."""
+        check(self.lib.ion_lbm_write_slice_png(self.handle, int(field), int(component), int(slice_mode), int(index), float(v_min),
+                                               float(v_max), str(path).encode()))
+
     def dump_cell(self, local_index, cell) -> str:
         out = ctypes.c_void_p()
         check(self.lib.ion_lbm_dump_cell(self.handle, local_index, cell, ctypes.byref(out)))

@@ -482,3 +482,82 @@ def test_full_size_mhd_charge_conservation(gpu_lib):
     assert np.isfinite(lod2).all()
     lbm.close()
     assert q0 > 0
+
+
+def _global_field(gpu, cfg, field, planes):
+    """Whole-lattice array [planes, Nz, Ny, Nx] assembled from the domains' buffers without halo layers (host-side reference
+    for the slice read-back)."""
+    out = np.zeros((planes, cfg.n_z, cfg.n_y, cfg.n_x), np.float32)
+    hx, hy, hz = int(cfg.d_x > 1), int(cfg.d_y > 1), int(cfg.d_z > 1)
+    for d in gpu.domains:
+        p = d.params
+        raw = d.read(field)
+        a = (raw.astype(np.float32) if raw.dtype == np.uint8 else raw).reshape(planes, p.nz, p.ny, p.nx)
+        sx, sy, sz = slice(hx, p.nx - hx), slice(hy, p.ny - hy), slice(hz, p.nz - hz)
+        out[:, p.oz + hz:p.oz + p.nz - hz, p.oy + hy:p.oy + p.ny - hy, p.ox + hx:p.ox + p.nx - hx] = a[:, sz, sy, sx]
+    return out
+
+
+def _decode_png_rgb(path):
+    import struct
+    import zlib
+    data = open(path, "rb").read()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, idat, w, h = 8, b"", 0, 0
+    while pos < len(data):
+        n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+        body = data[pos + 8:pos + 8 + n]
+        assert zlib.crc32(typ + body) == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0], "chunk CRC"
+        if typ == b"IHDR":
+            w, h, depth, ctype = struct.unpack(">IIBB", body[:10])
+            assert (depth, ctype) == (8, 2)
+        if typ == b"IDAT":
+            idat += body
+        pos += 12 + n
+    raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+    assert (raw[:, 0] == 0).all()
+    return raw[:, 1:].reshape(h, w, 3)
+
+
+@pytest.mark.parametrize("name", ["z3_d3q19_fp16s_trt", "x2y2_d3q27_fp32", "d3q19_fp32_srt"])
+def test_slice_read_back_and_png(name, gpu_lib, tmp_path):
+    """one plane of rho / u / flags gathered on the device equals the same plane of the full buffers (bit-exact, halo
+    layers removed, every slice mode), and the PNG writer produces a decodable RGB image coloured with the reference's iron map."""
+    from ionsolver_b200 import capi
+    cfg = dict(cases.single_domain_cases() + cases.multi_domain_cases())[name]
+    ref = rh.RefLbm(cfg, threads=1, backend="port")
+    cases.fill_inputs(ref, cfg)
+    gpu = product(cfg)
+    cases.upload_inputs(ref, gpu)
+    gpu.initialize()
+    gpu.do_time_step()
+    gpu.finish_queues()
+    u = _global_field(gpu, cfg, 2, 3)
+    rho = _global_field(gpu, cfg, 1, 1)[0]
+    flags = _global_field(gpu, cfg, 3, 1)[0]
+    for mode, n_axis, take in ((1, cfg.n_x, lambda a, i: a[..., :, :, i]), (2, cfg.n_y, lambda a, i: a[..., :, i, :]),
+                               (3, cfg.n_z, lambda a, i: a[..., i, :, :])):
+        for index in sorted({0, n_axis // 2, n_axis - 1}):
+            assert same_bits(gpu.read_slice(1, mode, index), take(rho, index)), (mode, index, "rho")
+            assert same_bits(gpu.read_slice(3, mode, index), take(flags, index)), (mode, index, "flags")
+            for comp in range(3):
+                assert same_bits(gpu.read_slice(2, mode, index, component=comp), take(u, index)[comp]), (mode, index, "u", comp)
+            mag = np.sqrt(take(u, index)[0] ** 2 + take(u, index)[1] ** 2 + take(u, index)[2] ** 2, dtype=np.float32)
+            assert np.allclose(gpu.read_slice(2, mode, index), mag, rtol=2e-7, atol=0)
+    # PNG: |u| on the middle z plane
+    v_max = float(np.sqrt((u ** 2).sum(0)).max()) or 1.0
+    path = tmp_path / "u.png"
+    gpu.write_slice_png(path, 2, 3, cfg.n_z // 2, 0.0, v_max)
+    img = _decode_png_rgb(path)
+    plane = gpu.read_slice(2, 3, cfg.n_z // 2)
+    assert img.shape == (cfg.n_y, cfg.n_x, 3)
+    lib = capi.load()
+    want = np.array([[lib.ion_iron_colormap(float(np.float32(v - np.float32(0.0)) * np.float32(1.0 / np.float32(v_max)))) for v in row]
+                     for row in plane[::-1]], np.uint32)
+    got = (img[..., 0].astype(np.uint32) << 16) | (img[..., 1].astype(np.uint32) << 8) | img[..., 2]
+    assert (got == want).mean() > 0.999  # the host multiplies by 1/(v_max - v_min) in float: allow a last-bit colour step
+    with pytest.raises(capi.IonError):
+        gpu.read_slice(2, 3, cfg.n_z)          # index outside the lattice
+    with pytest.raises(capi.IonError):
+        gpu.read_slice(0, 3, 0)                # fi is not a per-cell field
+    gpu.close()

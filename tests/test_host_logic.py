@@ -155,3 +155,50 @@ def test_ion_decode_rejects_bad_files_before_touching_the_gpu():
     assert c.float_type == L.FloatType.FP16C      # FILE_LAYOUT / types.rs discriminant
     lib.ion_lbm_decode(hdr, len(hdr), c, 1, None, 0, ctypes.byref(h))
     assert c.float_type == L.FloatType.FP16S      # the reference decoder's swapped table, file.rs:68-73
+
+
+def test_png_writer_and_iron_colormap(tmp_path):
+    """Host-only parts of the slice writer: the PNG encoder round-trips through zlib, and the colour map is the
+    reference's iron_colormap (graphics_kernels.cl:412-428 with color_from_floats :93-95)."""
+    import zlib
+    lib = capi.load()
+
+    def iron(x):  # graphics_kernels.cl:412-428 in float32
+        f = np.float32
+        x = f(min(max(f(4.0) * (f(1.0) - f(x)), f(0.0)), f(4.0)))
+        r, g, b = f(1.0), f(0.0), f(0.0)
+        if x < f(0.66666667):
+            g, b = f(1.0), f(1.0) - x * f(1.5)
+        elif x < f(2.0):
+            g = f(1.5) - x * f(0.75)
+        elif x < f(3.0):
+            r, b = f(2.0) - x * f(0.5), x - f(2.0)
+        else:
+            r, b = f(2.0) - x * f(0.5), f(4.0) - x
+        ch = lambda v: int(min(max(int(np.float32(255.0) * v + np.float32(0.5)), 0), 255))
+        return ch(r) << 16 | ch(g) << 8 | ch(b)
+
+    for x in np.linspace(-0.2, 1.2, 141):
+        got, want = lib.ion_iron_colormap(float(np.float32(x))), iron(np.float32(x))
+        assert all(abs(((got >> s) & 255) - ((want >> s) & 255)) <= 1 for s in (16, 8, 0)), (x, hex(got), hex(want))
+    assert lib.ion_iron_colormap(1.0) == 0xFFFFFF and lib.ion_iron_colormap(0.0) == 0x000000
+
+    rng = np.random.default_rng(5)
+    for w, h in ((1, 1), (7, 3), (300, 91)):  # the last one needs more than one stored deflate block (65535 bytes)
+        rgb = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        path = tmp_path / f"t{w}x{h}.png"
+        capi.check(lib.ion_write_png_rgb(str(path).encode(), rgb.ctypes.data, w, h))
+        data = path.read_bytes()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, idat = 8, b""
+        while pos < len(data):
+            n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+            body = data[pos + 8:pos + 8 + n]
+            assert zlib.crc32(typ + body) == struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])[0]
+            if typ == b"IHDR":
+                assert struct.unpack(">IIBBBBB", body) == (w, h, 8, 2, 0, 0, 0)
+            if typ == b"IDAT":
+                idat += body
+            pos += 12 + n
+        raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
+        assert (raw[:, 0] == 0).all() and (raw[:, 1:].reshape(h, w, 3) == rgb).all()
