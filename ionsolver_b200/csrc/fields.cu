@@ -454,16 +454,28 @@ __device__ __forceinline__ void pair_put(float2 (&e2)[NC / 2][3], float2 (&b2)[N
         if (2 * j + 1 == k) { e2[j][0].y = ek[0]; e2[j][1].y = ek[1]; e2[j][2].y = ek[2]; b2[j][0].y = bk[0]; b2[j][1].y = bk[1]; b2[j][2].y = bk[2]; }
     }
 }
+// ION_EB_MIX: how many of the nine packed FMAs per lane pair run as scalar FFMA pairs instead (see fma_pair)
+#ifndef ION_EB_MIX
+#define ION_EB_MIX 1
+#endif
 // nine FFMA2: e += q*p, b += w x p for two cells at once (same rounding sequence as accumulate_pair<false>)
 __device__ __forceinline__ void fma_pair(float2* e, float2* b, const float4 A, const float4 B, const float2 PX, const float2 PY, const float2 PZ) {
     const float2 q = make_float2(A.x, A.y), wx = make_float2(A.z, A.w), wy = make_float2(B.x, B.y), wz = make_float2(B.z, B.w);
     const float2 NX = make_float2(-PX.x, -PX.y), NY = make_float2(-PY.x, -PY.y), NZ = make_float2(-PZ.x, -PZ.y);
-    e[0] = __ffma2_rn(q, PX, e[0]);
-    e[1] = __ffma2_rn(q, PY, e[1]);
-    e[2] = __ffma2_rn(q, PZ, e[2]);
-    b[0] = __ffma2_rn(wy, PZ, __ffma2_rn(wz, NY, b[0]));
-    b[1] = __ffma2_rn(wz, PX, __ffma2_rn(wx, NZ, b[1]));
-    b[2] = __ffma2_rn(wx, PY, __ffma2_rn(wy, NX, b[2]));
+    // ION_EB_MIX = S: the last S of the nine packed FMAs (order: e0 e1 e2 | b first stage 0 1 2 | b second stage 0 1 2) are issued
+    // as two scalar FFMA each -- a scalar FFMA occupies the FMA pipe for 1 cycle per 32 FMAs, FFMA2 for 2.27 per 64, and the
+    // kernel has spare issue slots (measured at 256^3: S = 0 23.55 ms, S = 1 22.32, S = 2 22.71, S = 3 23.05, S = 4 24.16, S = 6 25.61)
+    auto f2 = [](float2 a, float2 b, float2 c, bool scalar) {
+        return scalar ? make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)) : __ffma2_rn(a, b, c);
+    };
+    constexpr int S = ION_EB_MIX;
+    e[0] = f2(q, PX, e[0], S >= 9);
+    e[1] = f2(q, PY, e[1], S >= 8);
+    e[2] = f2(q, PZ, e[2], S >= 7);
+    const float2 t0 = f2(wz, NY, b[0], S >= 6), t1 = f2(wx, NZ, b[1], S >= 5), t2 = f2(wy, NX, b[2], S >= 4);
+    b[0] = f2(wy, PZ, t0, S >= 3);
+    b[1] = f2(wz, PX, t1, S >= 2);
+    b[2] = f2(wx, PY, t2, S >= 1);
 }
 
 // VOL = true: every (step, lane pair) re-reads its source entry with a volatile LDS.128 (2 LDS per 9 FFMA2, few registers);
