@@ -124,7 +124,8 @@ template <int VS> __device__ __forceinline__ float cdot(int i, float ax, float a
 // normal results and, rounded TOWARD ZERO, lands results below 2^-14 on the float-denormal grid, which is the reference's
 // truncating shift; adding 0x800 to those bits and dropping 12 bits is then its round-half-up in both ranges (mantissa
 // carries ripple into the exponent field like in the reference, the 4-bit exponent wraps the same way, +-inf included).
-// Checked against fp16c_encode_ref for every non-NaN float on the CPU (2^32 - 2^24 inputs, round-toward-zero emulation) and
+// Checked against the reference formula for every non-NaN float on the CPU (tests/tools/fp16c_encode_check.c: 2^32 - 2^24 inputs,
+// host FPU in round-toward-zero mode; a strided run is part of the CPU test suite) and
 // on the device in tests/test_gpu_parity.py::test_codecs_exhaustive.  NaN inputs (a broken simulation) give a different
 // finite code than the reference's bit shuffle.
 __device__ __forceinline__ uint16_t fp16c_encode(float x) {

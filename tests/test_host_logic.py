@@ -202,3 +202,18 @@ def test_png_writer_and_iron_colormap(tmp_path):
             pos += 12 + n
         raw = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(h, 1 + 3 * w)
         assert (raw[:, 0] == 0).all() and (raw[:, 1:].reshape(h, w, 3) == rgb).all()
+
+
+def test_fp16c_encoder_identity_on_cpu(tmp_path):
+    """The device FP16C encoder is one round-toward-zero multiplication (lattice.cuh); tests/tools/fp16c_encode_check.c proves it
+    equal to the reference's bit assembly (sim_kernels.cl:79-84) with the host FPU in FE_TOWARDZERO mode.  Here: every 97th bit
+    pattern plus dense sweeps of the binade edges (the full 2^32 run takes a minute: `./fp16c_encode_check`)."""
+    import os
+    import subprocess
+    src = os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools", "fp16c_encode_check.c")
+    exe = tmp_path / "fp16c_encode_check"
+    subprocess.run(["gcc", "-O2", "-frounding-math", "-o", str(exe), src, "-lm"], check=True)
+    out = subprocess.run([str(exe), "97"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout[-500:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["mismatches_non_nan"] == 0 and res["checked"] > 44_000_000
