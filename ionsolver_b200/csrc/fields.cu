@@ -464,6 +464,12 @@ __device__ __forceinline__ void pair_put(float2 (&e2)[NC / 2][3], float2 (&b2)[N
 #ifndef ION_EB_NOGUARD
 #define ION_EB_NOGUARD 0
 #endif
+// Schedule experiments on the hot loop (A/B builds, update_e_b_dynamic at 256^3 depth 4; 0 = adopted: 22.07 ms):
+// 1 = lane pairs descending 23.48 ms, 2 = cross product interleaved with E 22.48, 3 = register cap 232 22.41,
+// 5 = r/|r|^3 with scalar FP32 22.57, 6 = step loop unrolled by 8 instead of 16 27.85.
+#ifndef ION_EB_EXP
+#define ION_EB_EXP 0
+#endif
 // nine FFMA2: e += q*p, b += w x p for two cells at once (same rounding sequence as accumulate_pair<false>)
 __device__ __forceinline__ void fma_pair(float2* e, float2* b, const float4 A, const float4 B, const float2 PX, const float2 PY, const float2 PZ) {
     const float2 q = make_float2(A.x, A.y), wx = make_float2(A.z, A.w), wy = make_float2(B.x, B.y), wz = make_float2(B.z, B.w);
@@ -476,6 +482,16 @@ __device__ __forceinline__ void fma_pair(float2* e, float2* b, const float4 A, c
     };
     constexpr int S = ION_EB_MIX;
 #if ION_EB_MIX_FIRST  // scalarise from the front (e0 first; measured S = 1: 22.07 ms) instead of from the back (22.30 ms)
+#if ION_EB_EXP == 2
+    const float2 v0 = f2(wz, NY, b[0], S >= 4), v1 = f2(wx, NZ, b[1], S >= 5), v2 = f2(wy, NX, b[2], S >= 6);
+    e[0] = f2(q, PX, e[0], S >= 1);
+    b[0] = f2(wy, PZ, v0, S >= 7);
+    e[1] = f2(q, PY, e[1], S >= 2);
+    b[1] = f2(wz, PX, v1, S >= 8);
+    e[2] = f2(q, PZ, e[2], S >= 3);
+    b[2] = f2(wx, PY, v2, S >= 9);
+    return;
+#endif
     e[0] = f2(q, PX, e[0], S >= 1);
     e[1] = f2(q, PY, e[1], S >= 2);
     e[2] = f2(q, PZ, e[2], S >= 3);
@@ -505,8 +521,13 @@ template <bool VOL> __device__ __forceinline__ float4 lds128(const float4* p) {
     return *p;
 }
 
+#if ION_EB_EXP == 3
+#define ION_EB_BOUNDS(B) __maxnreg__(232)
+#else
+#define ION_EB_BOUNDS(B) __launch_bounds__(B, 1)
+#endif
 template <int ND, int NC, int BLOCK, bool VOL>
-__global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
+__global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
                                                                 const uint32_t n_foreign, const __grid_constant__ ForeignSet fs) {
     static_assert(ND % NC == 0 && NC % 2 == 0, "cells per thread");
     constexpr int PARTS = ND / NC;
@@ -615,12 +636,20 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
         const float4* __restrict__ srow = s_pair + 2 * d0;
         const int self_dl = is_self ? -(int)kbase : 0x7fffffff;  // local diagonal of the own block (true diagonal 0)
         const float ryz2 = fmaf(ry, ry, rz * rz);
+#if ION_EB_EXP == 6
+#pragma unroll 8
+#else
 #pragma unroll
+#endif
         for (int Dp = 0; Dp < ND; Dp++) {
             // hi (.y): cells kl >= D' on local diagonal D'; lo (.x): cells kl < D' on local diagonal D' - ND.  Both r/|r|^3
             // vectors are evaluated together with packed FP32 (same roundings as pre_field<false>).
             const float2 rx = make_float2((float)(Dp - ND) * dsxf + rx0, (float)Dp * dsxf + rx0);
+#if ION_EB_EXP == 5
+            const float2 r2 = make_float2(fmaf(rx.x, rx.x, ryz2), fmaf(rx.y, rx.y, ryz2));
+#else
             const float2 r2 = __ffma2_rn(rx, rx, make_float2(ryz2, ryz2));
+#endif
 #if ION_EB_NOGUARD
             // r = 0 can only occur on the self-skipped pair of the self row (the one source whose coordinates are the cell's own
             // block, see the comment above k_update_e_b_tiled), where ri3 is overwritten with 0 below.  Measured SLOWER (24.7 vs
@@ -629,12 +658,21 @@ __global__ void __launch_bounds__(BLOCK, 1) k_update_e_b_pair(const __grid_const
 #else
             const float2 ri = make_float2(r2.x > 0.0f ? rsqrtf(r2.x) : 0.0f, r2.y > 0.0f ? rsqrtf(r2.y) : 0.0f);
 #endif
+#if ION_EB_EXP == 5
+            float2 ri3 = make_float2(ri.x * ri.x * ri.x, ri.y * ri.y * ri.y);
+#else
             float2 ri3 = __fmul2_rn(__fmul2_rn(ri, ri), ri);
+#endif
             if (Dp - ND == self_dl) ri3.x = 0.0f;  // the own block contributes nothing (sim.cl:944)
             if (Dp == self_dl) ri3.y = 0.0f;
+#if ION_EB_EXP == 5
+            const float2 px = make_float2(rx.x * ri3.x, rx.y * ri3.y), py = make_float2(ry * ri3.x, ry * ri3.y), pz = make_float2(rz * ri3.x, rz * ri3.y);
+#else
             const float2 px = __fmul2_rn(rx, ri3), py = __fmul2_rn(make_float2(ry, ry), ri3), pz = __fmul2_rn(make_float2(rz, rz), ri3);
+#endif
 #pragma unroll
-            for (int j = 0; j < NC / 2; j++) {
+            for (int jj = 0; jj < NC / 2; jj++) {
+                const int j = ION_EB_EXP == 1 ? NC / 2 - 1 - jj : jj;
                 const int t = ((2 * j - Dp) % ND + ND) % ND;  // source of lane .x; lane .y uses its cyclic successor
                 const float4 A = lds128<VOL>(srow + 2 * t), B = lds128<VOL>(srow + 2 * t + 1);
                 const bool xh = 2 * j >= Dp, yh = 2 * j + 1 >= Dp;
