@@ -113,11 +113,13 @@ class ClockSampler:
     """nvidia-smi clocks line of B200_PROFILING.md, sampled DURING the timed region."""
 
     def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz, self.stop = [], set(), None, threading.Event()
+        self.samples, self.reasons, self.max_mhz, self.stop, self.source = [], set(), None, threading.Event(), "nvidia-smi"
         self.index = index
         self.thread = threading.Thread(target=self._run, daemon=True)
 
     def _run(self):
+        if self._run_nvml():
+            return
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -134,6 +136,34 @@ class ClockSampler:
                 pass
             self.stop.wait(0.1)
 
+    def _run_nvml(self):
+        """Same quantities through NVML (nvidia_ml_py): a query takes microseconds, so a 0.5 s timed region gets ~50 samples instead
+        of the one or two an nvidia-smi process manages.  Returns False (-> nvidia-smi loop) when NVML is not usable."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.index]) if visible and visible.split(",")[self.index].strip().isdigit() else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        self.source = "nvml"
+        while not self.stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for b, n in bits.items():
+                    if r & b:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self.stop.wait(0.01)
+        return True
+
     def __enter__(self):
         self.thread.start()
         return self
@@ -144,7 +174,8 @@ class ClockSampler:
 
     def summary(self):
         return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "sm_mhz_min": float(np.min(self.samples)) if self.samples else None,
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 def build_scene(args, rank, world, device):
