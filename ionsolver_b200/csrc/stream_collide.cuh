@@ -460,6 +460,10 @@ cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt,
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
 
+// four-cells-per-thread vector variant of the plain kernel (stream_collide_v4.cuh); returns false when it does not apply
+template <int VS>
+inline bool launch_stream_collide_v4(const KArgs& a, int fp, bool trt, uint64_t t, float fx, float fy, float fz, cudaStream_t s);
+
 #define ION_SC_CASE(FPV, MHDV, TRTV, ECRV)                                                                 \
     if (fp == FPV && mhd == MHDV && trt == TRTV && ecr == ECRV) {                                          \
         if (t & 1ull) k_stream_collide<VS, FPV, MHDV, TRTV, ECRV, true><<<grid, block, 0, s>>>(a, fx, fy, fz);  \
@@ -472,6 +476,7 @@ template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool 
     cudaError_t launch_stream_collide_vs<VSV>(const KArgs& a, int fp, bool mhd, bool trt, bool ecr, uint64_t t,      \
                                               float fx, float fy, float fz, cudaStream_t s) {                        \
         constexpr int VS = VSV;                                                                                      \
+        if (!mhd && !ecr && launch_stream_collide_v4<VSV>(a, fp, trt, t, fx, fy, fz, s)) return cudaGetLastError();  \
         unsigned block;                                                                                              \
         const dim3 grid = sc_grid(a, block);                                                                         \
         ION_SC_CASE(ION_FP32, false, false, false)                                                                   \

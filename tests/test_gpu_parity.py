@@ -561,3 +561,22 @@ def test_slice_read_back_and_png(name, gpu_lib, tmp_path):
     with pytest.raises(capi.IonError):
         gpu.read_slice(0, 3, 0)                # fi is not a per-cell field
     gpu.close()
+
+
+def test_vector_kernel_parity_on_every_configuration(gpu_lib):
+    """The four-cells-per-thread stream_collide (stream_collide_v4.cuh) is the default only for FP32, Q <= 19, nx >= 256; with
+    ION_SC_VEC=1 it runs wherever nx % 4 == 0.  The library reads the switch once, so the bit-exact single- and multi-domain parity
+    tests (all velocity sets, storage codecs, SRT/TRT, equilibrium boundaries, force field, split x/y/z) are re-run in a child
+    process with the switch set."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("ION_SC_VEC"):
+        pytest.skip("already inside the forced run")
+    env = dict(os.environ, ION_SC_VEC="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k",
+                          "test_single_domain_bit_exact or test_multi_domain_bit_exact or test_ion_file_round_trip"],
+                         env=env, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
+    assert " passed" in out.stdout
