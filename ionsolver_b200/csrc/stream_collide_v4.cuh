@@ -114,6 +114,9 @@ __device__ __forceinline__ void plain_cell(const KArgs& a, uint32_t n, uint8_t f
     }
 }
 
+// 6 resident blocks of 64 threads per SM (168 registers, no spills for Q <= 19).  Also measured: D3Q27 at 4 blocks / 254 registers
+// 0.759 (one-cell kernel 0.823), FP16S / FP16C at 8 blocks / 128 registers 0.503 / 0.393 (6 blocks: 0.507 / 0.381) -- neither beats
+// the one-cell kernels, so only FP32 with Q <= 19 uses this kernel by default.
 template <int VS, int FP, bool TRT, bool ODD>
 __global__ void __launch_bounds__(64, 6)
 k_stream_collide_v4(const __grid_constant__ KArgs a, const float fx, const float fy, const float fz) {
