@@ -3,18 +3,22 @@
 //
 // Behaviour follows /root/reference/src/kernels/sim_kernels.cl ("sim.cl"): stream_collide :465-758,
 // initialize :760-832, update_fields :834-859.  Design for B200 (sm_100a):
-//   * one thread per lattice cell, x fastest: every DDF access of a warp is one contiguous 128 B (FP32) /
-//     64 B (FP16) segment per direction -- the SoA layout i*N+n keeps all 2Q(+2Q+14) streams coalesced;
-//   * Esoteric-Pull in-place streaming: each (cell,slot) address is read and then written by the same
-//     thread, so no second DDF copy exists and algorithmic HBM traffic is the minimum 2*Q*s bytes/cell;
-//   * 3-D launch (x-chunk, y, z): no integer div/mod per cell, branch-free periodic wraps;
-//   * all loads of a cell (19+19+7 DDFs, E, B, flags) are issued before first use -> >50 independent
-//     requests in flight per thread, which is what saturates HBM3e at modest occupancy;
-//   * MHD source terms (electron-gas LBM, D3Q7 charge advection, Lorentz force) are applied in registers;
-//     the LOD deposit is a warp-segmented shuffle reduction followed by one red.global per (warp, LOD block)
-//     instead of the reference's 4 same-address atomics per cell (sim.cl:673-676);
+//   * one thread per lattice cell, x fastest: every DDF access of a warp is one contiguous 128 B (FP32) / 64 B (FP16) segment per
+//     direction -- the SoA layout i*N+n keeps all 2Q(+2Q+14) streams coalesced (the plain FP32 kernels use the four-cells-per-thread
+//     variant with 128-bit accesses of stream_collide_v4.cuh);
+//   * Esoteric-Pull in-place streaming: each (cell,slot) address is read and then written by the same thread, so no second DDF copy
+//     exists and algorithmic HBM traffic is the minimum 2*Q*s bytes/cell;
+//   * 3-D launch (x-chunk, y, z): no integer div/mod per cell, branch-free periodic wraps; the step parity is a template parameter,
+//     so slot indices are constants and an address costs two integer instructions;
+//   * all loads of a cell (19+19+7 DDFs, E, B) are pinned in program order IN FRONT of the branch on the flag byte (ptxas would sink
+//     them below it) -> >50 independent requests in flight per thread, which is what saturates HBM3e at modest occupancy;
+//   * MHD source terms (electron-gas LBM, D3Q7 charge advection, Lorentz force) are applied in registers; the neutral gas and the
+//     electron gas share the two lanes of packed FP32 (collide_two_species, lattice.cuh);
+//   * the LOD deposit is a warp-segmented shuffle reduction followed by one 16-byte vector reduction per (warp, LOD block) into one
+//     of 32 private replicas (same-address reductions serialise in L2) instead of the reference's 4 same-address atomics per cell
+//     (sim.cl:673-676);
 //   * EQUILIBRIUM_BOUNDARIES / VOLUME_FORCE / FORCE_FIELD / UPDATE_FIELDS are warp-uniform runtime switches
-//     (they do not change register pressure materially); Q, storage codec, MHD and TRT are compile time.
+//     (they do not change register pressure materially); Q, storage codec, MHD, TRT and the step parity are compile time.
 // No tensor cores: the kernel is HBM-bound (153 B/cell plain, 389 B/cell MHD for D3Q19 FP32).
 #pragma once
 #include <cstdlib>
