@@ -116,6 +116,24 @@ def ecr_cases():
     ]
 
 
+def extra_oracle_cases():
+    """Oracle-only pins (CPU, live reference build): combinations of velocity set / collision / storage / extensions that the
+    golden matrix above does not contain, so that the C restatement is compared with the reference's own kernels on them too."""
+    return [
+        ("x_d3q15_fp32_srt_eqb_ff_vf", C(velocity_set="D3Q15", float_type="FP32", n_x=19, n_y=11, n_z=7, nu=0.03, ext_equilibrium_boudaries=True,
+                                         ext_volume_force=True, ext_force_field=True, f_x=2e-4, f_z=-1e-4, graphics_active=True)),
+        ("x_d2q9_fp16c_trt", C(velocity_set="D2Q9", float_type="FP16C", relaxation_time="TRT", n_x=28, n_y=18, n_z=1, nu=0.04, graphics_active=True)),
+        ("x_d3q27_fp32_trt_ff", C(velocity_set="D3Q27", float_type="FP32", relaxation_time="TRT", n_x=12, n_y=10, n_z=8, nu=0.06,
+                                  ext_volume_force=True, ext_force_field=True, f_y=1e-4)),
+        ("x_mhd_d3q19_fp32_trt_lod2", _mhd(C(velocity_set="D3Q19", float_type="FP32", relaxation_time="TRT", n_x=16, n_y=16, n_z=16, nu=0.05,
+                                             ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True), 16.0)),
+        ("x_mhd_d3q15_fp16c_lod2", _mhd(C(velocity_set="D3Q15", float_type="FP16C", n_x=16, n_y=12, n_z=8, nu=0.05, ext_volume_force=True,
+                                          ext_magneto_hydro=True, mhd_lod_depth=2), 16.0)),
+        ("x_y2_d3q19_fp16c_trt", C(velocity_set="D3Q19", float_type="FP16C", relaxation_time="TRT", n_x=10, n_y=16, n_z=6, d_y=2, nu=0.05,
+                                   ext_volume_force=True, f_x=1e-4, graphics_active=True)),
+    ]
+
+
 def all_cases():
     return single_domain_cases() + mhd_cases() + multi_domain_cases() + multi_domain_mhd_cases() + ecr_cases()
 

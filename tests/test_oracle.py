@@ -53,6 +53,28 @@ def test_port_matches_live_reference_build(name, cfg):
             assert same_bits(getattr(da, n), getattr(db, n)), f"domain {da.g.d_i} buffer {n}"
 
 
+EXTRA = cases.extra_oracle_cases()
+
+
+@pytest.mark.skipif(not have_reference(), reason="/root/reference absent: live reference build unavailable")
+@pytest.mark.parametrize("name,cfg", EXTRA, ids=[c[0] for c in EXTRA])
+def test_port_matches_live_reference_build_on_extra_combinations(name, cfg):
+    """MHD with TRT, D3Q15 / D2Q9 with the compressed codecs, D3Q27 TRT with a force field, a y-split: the restatement against
+    the reference's kernels compiled on the spot, every buffer bit for bit after initialize + 4 steps."""
+    a = rh.RefLbm(cfg, threads=1)
+    b = rh.RefLbm(cfg, threads=1, backend="port")
+    cases.fill_inputs(a, cfg, seed=9)
+    cases.fill_inputs(b, cfg, seed=9)
+    for lbm in (a, b):
+        lbm.initialize()
+        if cfg.ext_magneto_hydro:
+            cases.seed_electron_gas(lbm)
+        lbm.run(4)
+    for da, db in zip(a.domains, b.domains):
+        for n in buffer_names(cfg):
+            assert same_bits(getattr(da, n), getattr(db, n)), f"domain {da.g.d_i} buffer {n}"
+
+
 def test_codecs_against_golden(golden):
     g = golden["codecs"]
     rng = np.random.default_rng(7)
