@@ -126,7 +126,7 @@ def extra_oracle_cases():
         ("x_d3q27_fp32_trt_ff", C(velocity_set="D3Q27", float_type="FP32", relaxation_time="TRT", n_x=12, n_y=10, n_z=8, nu=0.06,
                                   ext_volume_force=True, ext_force_field=True, f_y=1e-4)),
         ("x_mhd_d3q19_fp32_trt_lod2", _mhd(C(velocity_set="D3Q19", float_type="FP32", relaxation_time="TRT", n_x=16, n_y=16, n_z=16, nu=0.05,
-                                             ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True), 16.0)),
+                                             ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=2, graphics_active=True), 16.0, weak=True)),
         ("x_mhd_d3q15_fp16c_lod2", _mhd(C(velocity_set="D3Q15", float_type="FP16C", n_x=16, n_y=12, n_z=8, nu=0.05, ext_volume_force=True,
                                           ext_magneto_hydro=True, mhd_lod_depth=2), 16.0)),
         ("x_y2_d3q19_fp16c_trt", C(velocity_set="D3Q19", float_type="FP16C", relaxation_time="TRT", n_x=10, n_y=16, n_z=6, d_y=2, nu=0.05,
