@@ -576,7 +576,7 @@ def test_vector_kernel_parity_on_every_configuration(gpu_lib):
     env = dict(os.environ, ION_SC_VEC="1")
     here = os.path.dirname(os.path.abspath(__file__))
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-x", "-q", "-k",
-                          "test_single_domain_bit_exact or test_multi_domain_bit_exact or test_ion_file_round_trip"],
+                          "test_single_domain_bit_exact or test_multi_domain_bit_exact or test_ion_file_round_trip or test_extra_combinations_bit_exact"],
                          env=env, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-1000:]
     assert " passed" in out.stdout
