@@ -213,8 +213,8 @@ k_stream_collide_v4(const __grid_constant__ KArgs a, const float fx, const float
 
 // Where it is used.  Measured at 256^3 / 512^3 (profiles/r1_stream_collide_ab.md, fraction of the HBM copy peak, one-cell -> four-cell):
 // D3Q19 FP32 SRT 0.869 -> 0.972 (512^3: 0.867 -> 0.969), TRT 0.723 -> 0.761; FP16S unchanged (0.51), FP16C slower (0.447 -> 0.381:
-// four encoders per thread), D3Q27 FP32 slower (0.823 -> 0.675: 4 x 27 live values against the 168-register cap), 64^3 slower (only 16
-// threads per x row).  Default: FP32, Q <= 19, nx >= 256.  ION_SC_VEC=1 forces it wherever nx % 4 == 0 (the parity tests use this to
+// four encoders per thread), D3Q27 FP32 slower (0.823 -> 0.675: 4 x 27 live values against the 168-register cap), 64^3 slower (8.5 us
+// -> 14.9 us with 16 threads per x row; 12.3 us with 16 x 4 thread blocks: 65 536 threads are less than one wave of the GPU).  Default: FP32, Q <= 19, nx >= 256.  ION_SC_VEC=1 forces it wherever nx % 4 == 0 (the parity tests use this to
 // run every configuration through it), ION_SC_VEC=0 turns it off.
 inline int sc_vec_mode() {
     static const int mode = getenv("ION_SC_VEC") ? (atoi(getenv("ION_SC_VEC")) != 0 ? 1 : 0) : -1;
