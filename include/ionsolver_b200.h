@@ -156,6 +156,9 @@ ION_API int ion_enqueue_initialize(ion_domain_t* dom);                          
 ION_API int ion_enqueue_stream_collide(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz); /* domain.rs:419-428 */
 ION_API int ion_enqueue_update_fields(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz);  /* domain.rs:432-441 */
 ION_API int ion_enqueue_update_e_b_dyn(ion_domain_t* dom);                                      /* domain.rs:443-451 */
+/* no reference counterpart: size of the static kernel spectra of the polyphase-FFT field update (0 = direct kernels in use)
+ * and the number of polyphase problems per step; valid after the first ion_enqueue_update_e_b_dyn */
+ION_API int ion_domain_eb_fft_info(const ion_domain_t* dom, uint64_t* spectrum_bytes, uint32_t* tasks);
 ION_API int ion_enqueue_lod_part_2_gather(ion_domain_t* dom);                                   /* domain.rs:453-462 */
 ION_API int ion_enqueue_clear_qu_lod(ion_domain_t* dom);                                        /* domain.rs:464-472 */
 /* transfer kernels only (the host read/write halves of domain.rs:484-543 are ion_buffer_read/write/copy on

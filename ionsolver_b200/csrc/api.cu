@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -19,6 +20,12 @@ cudaError_t launch_stream_collide_vs(const KArgs& a, int fp, bool mhd, bool trt,
 template <int VS> cudaError_t launch_update_fields_vs(const KArgs& a, int fp, uint64_t t, cudaStream_t s);
 template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool mhd, cudaStream_t s);
 cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, bool exact);
+cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches);
+cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, EbFftPlan** out, uint64_t* launches);
+cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches);
+void eb_fft_destroy(EbFftPlan* p);
+size_t eb_fft_plan_bytes(const EbFftPlan* p);
+uint32_t eb_fft_plan_tasks(const EbFftPlan* p);
 cudaError_t launch_lod_fold(const KArgs& a, cudaStream_t s);
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di);
 cudaError_t launch_clear_qu_lod(const KArgs& a, cudaStream_t s);
@@ -333,6 +340,7 @@ int ion_domain_destroy(ion_domain_t* d) {
     for (int f = 0; f < ION_FIELD_COUNT; f++)
         if (d->buf[f]) cudaFree(d->buf[f]);
     if (d->lod_sources) cudaFree(d->lod_sources);
+    if (d->eb_plan) eb_fft_destroy(d->eb_plan);
     if (d->cp_counts) cudaFree(d->cp_counts);
     if (d->lod_u) cudaFree(d->lod_u);
     if (d->lod_rep) cudaFree(d->lod_rep);
@@ -539,9 +547,36 @@ int ion_enqueue_update_e_b_dyn(ion_domain_t* d) {
     if (r) return r;
     ION_CUDA(cudaSetDevice(d->device));
     uint64_t l = 0;
-    cudaError_t e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l, d->deterministic);
+    cudaError_t e;
+    // Default path: the own pyramid as a polyphase FFT convolution (eb_fft.cu) when the geometry allows it and the static
+    // kernel spectra (102 B per cell) fit in half of the free device memory (ION_EB_FFT=0 keeps the direct kernels,
+    // ION_EB_FFT_MAX_GB overrides the budget).  The deterministic mode always uses the reference-ordered direct kernel.
+    if (!d->deterministic && !d->eb_plan_tried) {
+        d->eb_plan_tried = true;
+        const char* sw = getenv("ION_EB_FFT");
+        if (!sw || atoi(sw) != 0) {
+            size_t free_b = 0, total_b = 0;
+            ION_CUDA(cudaMemGetInfo(&free_b, &total_b));
+            size_t budget = free_b / 2;
+            if (const char* gb = getenv("ION_EB_FFT_MAX_GB")) budget = (size_t)(atof(gb) * 1073741824.0);
+            e = eb_fft_create(d->k, budget, d->stream, &d->eb_plan, &l);
+            if (e != cudaSuccess) return cuda_fail(e, "update_e_b_dynamic: building the kernel spectra");
+        }
+    }
+    if (d->eb_plan && !d->deterministic) {
+        e = eb_fft_launch(d->eb_plan, d->k, d->stream, &l);
+        if (e == cudaSuccess) e = launch_update_e_b_foreign(d->k, d->lod_sources, d->stream, &l);
+    } else {
+        e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l, d->deterministic);
+    }
     g_launches += l;
     if (e != cudaSuccess) return cuda_fail(e, "update_e_b_dynamic launch");
+    return ION_OK;
+}
+int ion_domain_eb_fft_info(const ion_domain_t* d, uint64_t* spectrum_bytes, uint32_t* tasks) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (spectrum_bytes) *spectrum_bytes = eb_fft_plan_bytes(d->eb_plan);
+    if (tasks) *tasks = eb_fft_plan_tasks(d->eb_plan);
     return ION_OK;
 }
 int ion_enqueue_lod_part_2_gather(ion_domain_t* d) {

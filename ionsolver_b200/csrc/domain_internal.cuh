@@ -6,6 +6,7 @@
 
 #include "lattice.cuh"
 
+namespace ion { struct EbFftPlan; }
 struct ion_domain {
     IonParams params;
     int device;
@@ -28,6 +29,8 @@ struct ion_domain {
     bool halo_active;
     float ecrf;
     bool deterministic;   // ION_EXT_DETERMINISTIC: reference-ordered LOD sums and reference arithmetic in update_e_b_dynamic
+    ion::EbFftPlan* eb_plan;  // polyphase-FFT update_e_b_dynamic (eb_fft.cu): static kernel spectra, built on first use
+    bool eb_plan_tried;
 };
 
 #ifndef ION_LOD_REPLICAS

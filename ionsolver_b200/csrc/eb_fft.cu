@@ -1,0 +1,196 @@
+// eb_fft.cu -- update_e_b_dynamic (sim_kernels.cl:897-993) as a polyphase FFT convolution: kernels, plan, launcher.
+// The algorithm, its layouts and the phase functions are in eb_fft_core.cuh; this file only wraps them into kernels.
+//
+//   k_eb_khat  (once per geometry)  K^_o for every task (in-block offset, z window), 3 components       -> HBM, static
+//   k_eb_src   (every step)         s^_j of the LOD source table (q, q v), H x 4 blocks                  -> L2 resident
+//   k_eb_fft   (every step)         one block per task: products, 2-D inverse FFT in shared memory, Hermitian DFT along x,
+//                                   E_dyn / B_dyn = static + k * sum   (sim.cl:986-992)
+#include <cstdlib>
+#include <vector>
+
+#include "eb_fft_core.cuh"
+#include "lattice.cuh"
+
+namespace ion {
+using namespace ebfft;
+
+struct EbFftPlan {
+    int nd;
+    uint32_t ntasks;
+    Geom g;
+    Task* tasks;
+    float2* khat;
+    float2* shat;
+    size_t khat_bytes;
+};
+
+template <int ND> __global__ void __launch_bounds__(256) k_eb_khat(const __grid_constant__ Geom g, const Task* __restrict__ tasks, float2* __restrict__ khat) {
+    extern __shared__ __align__(16) unsigned char eb_smem[];
+    float2* S = reinterpret_cast<float2*>(eb_smem);
+    const int task = blockIdx.x, comp = blockIdx.y;
+    const Task t = tasks[task];
+    khat_phase_x<ND>(threadIdx.x, blockDim.x, g, t, comp, S);
+    __syncthreads();
+    khat_phase_y<ND>(threadIdx.x, blockDim.x, S);
+    __syncthreads();
+    khat_phase_z<ND>(threadIdx.x, blockDim.x, task, comp, S, khat);
+}
+
+template <int ND> __global__ void __launch_bounds__(128) k_eb_src(const __grid_constant__ Geom g, const float* __restrict__ QU_lod, float2* __restrict__ shat) {
+    __shared__ float2 plane[Cfg<ND>::M * Cfg<ND>::ROW];
+    const int kx = blockIdx.x, j = blockIdx.y;
+    src_phase_x<ND>(threadIdx.x, blockDim.x, g, QU_lod, kx, j, plane);
+    __syncthreads();
+    src_phase_y<ND>(threadIdx.x, blockDim.x, plane);
+    __syncthreads();
+    src_phase_z<ND>(threadIdx.x, blockDim.x, kx, j, plane, shat);
+}
+
+template <int ND>
+__global__ void __launch_bounds__(Cfg<ND>::T, 1)
+    k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
+             const uint8_t* __restrict__ flags, const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
+             float* __restrict__ B_dyn) {
+    typedef Cfg<ND> C;
+    extern __shared__ __align__(16) unsigned char eb_smem[];
+    float2* W = reinterpret_cast<float2*>(eb_smem);
+    float2* tw = W + (size_t)C::P * C::PLANE;
+    const int tid = threadIdx.x;
+    if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
+    const Task t = tasks[blockIdx.x];
+    const float2* kt = khat + (size_t)blockIdx.x * C::khat_per_task;
+    float acc[6][C::XPT];
+#pragma unroll
+    for (int s = 0; s < 6; s++)
+#pragma unroll
+        for (int i = 0; i < C::XPT; i++) acc[s][i] = 0.0f;
+    for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
+        const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
+        main_phase_product<ND, 1>(tid, kt, shat, nullptr, nullptr, kx0, np, W);
+        __syncthreads();
+        main_phase_z<ND>(tid, np, W);
+        __syncthreads();
+        main_phase_y<ND>(tid, np, W);
+        __syncthreads();
+        main_phase_accumulate<ND>(tid, kx0, np, W, tw, acc);
+        __syncthreads();
+    }
+    main_phase_write<ND>(tid, g, t, flags, E_stat, B_stat, E_dyn, B_dyn, acc);
+}
+
+// The polyphase path needs: LOD depth 3 or 4, x and y extents that are whole LOD blocks (z may carry the two halo layers of a
+// slab: they become an extra z window), the full fine level inside the pyramid.  Everything else stays on fields.cu's kernels.
+bool eb_fft_supported(const KArgs& a) {
+    if (a.lod_depth != 3u && a.lod_depth != 4u) return false;
+    const uint32_t nd = 1u << a.lod_depth;
+    if (a.nx % nd || a.ny % nd || a.nz < nd) return false;
+    if (a.n_lod_own < nd * nd * nd) return false;
+    if (a.dx > 1u || a.dy > 1u) return false;  // halo layers in x / y would make the blocks ragged
+    // the near-cell loop of sim.cl:907-938 must be empty (quirk Q4: block = N / 2^(2^depth); true for every lattice below 512
+    // cells per axis at depth 3 and always at depth 4)
+    const uint32_t sh = 1u << nd;
+    if ((a.nx / sh > 1u) || (a.ny / sh > 1u) || (a.nz / sh > 1u)) return false;
+    const uint32_t dsz = a.nz / nd;
+    if (a.nz - nd * dsz >= dsz) return false;  // more than one extra z window cannot happen (nz < (nd+1)*dsz), but be explicit
+    return true;
+}
+
+static void eb_fft_geometry(const KArgs& a, Geom& g, std::vector<Task>& tasks) {
+    const uint32_t nd = 1u << a.lod_depth;
+    g.nx = a.nx; g.ny = a.ny; g.nz = a.nz; g.N = a.N;
+    g.dsx = a.nx / nd; g.dsy = a.ny / nd; g.dsz = a.nz / nd;
+    g.n_lod_own = a.n_lod_own;
+    g.lo = a.n_lod_own - nd * nd * nd;
+    g.cz0 = g.lo / (nd * nd);
+    g.dx = a.dx; g.dy = a.dy; g.dz = a.dz;
+    g.ke = a.ke; g.kmu = a.kmu;
+    const uint32_t nwz = (a.nz + nd * g.dsz - 1u) / (nd * g.dsz);
+    for (uint32_t wz = 0; wz < nwz; wz++)
+        for (uint32_t oz = 0; oz < g.dsz; oz++) {
+            // does this (window, oz) hold any cell that update_e_b_dynamic writes?  (z < nz, not a halo layer)
+            bool any = false;
+            for (uint32_t bz = 0; bz < nd && !any; bz++) {
+                const uint32_t z = (bz + nd * wz) * g.dsz + oz;
+                if (z >= a.nz) break;
+                any = !(a.dz > 1u && (z == 0u || z >= a.nz - 1u));
+            }
+            if (!any) continue;
+            // ox fastest: blocks that run at the same time write neighbouring words of the same sectors, which L2 merges
+            for (uint32_t oy = 0; oy < g.dsy; oy++)
+                for (uint32_t ox = 0; ox < g.dsx; ox++) tasks.push_back(Task{(uint16_t)ox, (uint16_t)oy, (uint16_t)oz, (uint16_t)wz});
+        }
+}
+
+size_t eb_fft_bytes(const KArgs& a) {
+    if (!eb_fft_supported(a)) return 0;
+    Geom g;
+    std::vector<Task> tasks;
+    eb_fft_geometry(a, g, tasks);
+    const size_t per = a.lod_depth == 4u ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
+    return tasks.size() * per * sizeof(float2);
+}
+
+void eb_fft_destroy(EbFftPlan* p) {
+    if (!p) return;
+    if (p->tasks) cudaFree(p->tasks);
+    if (p->khat) cudaFree(p->khat);
+    if (p->shat) cudaFree(p->shat);
+    delete p;
+}
+
+template <int ND> static cudaError_t build_khat(EbFftPlan* p, cudaStream_t s) {
+    cudaError_t e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
+    if (e != cudaSuccess) return e;
+    k_eb_khat<ND><<<dim3(p->ntasks, 3), 256, Cfg<ND>::khat_smem, s>>>(p->g, p->tasks, p->khat);
+    return cudaGetLastError();
+}
+
+// Builds the static part (task list, K^) on the domain's device.  *out = nullptr (and cudaSuccess) when the geometry is not
+// supported or the spectra do not fit `budget_bytes`.
+cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, EbFftPlan** out, uint64_t* launches) {
+    *out = nullptr;
+    if (!eb_fft_supported(a)) return cudaSuccess;
+    EbFftPlan* p = new EbFftPlan();
+    p->nd = 1 << a.lod_depth;
+    p->tasks = nullptr; p->khat = nullptr; p->shat = nullptr;
+    std::vector<Task> tasks;
+    eb_fft_geometry(a, p->g, tasks);
+    p->ntasks = (uint32_t)tasks.size();
+    const size_t per = p->nd == 16 ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
+    const size_t sh = p->nd == 16 ? Cfg<16>::shat_count : Cfg<8>::shat_count;
+    p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
+    if (p->khat_bytes > budget_bytes) { delete p; return cudaSuccess; }
+    cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->khat, p->khat_bytes);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->shat, sh * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(p->tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `tasks` is a local vector
+    if (e == cudaSuccess) e = p->nd == 16 ? build_khat<16>(p, s) : build_khat<8>(p, s);
+    if (e != cudaSuccess) {
+        eb_fft_destroy(p);
+        if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return cudaSuccess; }  // no room: the direct kernels stay in charge
+        return e;
+    }
+    (*launches)++;
+    *out = p;
+    return cudaSuccess;
+}
+
+template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& a, cudaStream_t s) {
+    // function attributes are per device: set on every launch (a host-side table lookup)
+    cudaError_t e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
+    if (e != cudaSuccess) return e;
+    k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, a.QU_lod, p->shat);
+    k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn);
+    return cudaGetLastError();
+}
+cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
+    *launches += 2;
+    return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
+}
+size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }
+uint32_t eb_fft_plan_tasks(const EbFftPlan* p) { return p ? p->ntasks : 0; }
+
+}  // namespace ion

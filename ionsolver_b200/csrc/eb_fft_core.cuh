@@ -1,0 +1,388 @@
+// eb_fft_core.cuh -- update_e_b_dynamic as a polyphase FFT convolution (the bodies of the kernels in eb_fft.cu).
+//
+// Behaviour: /root/reference/src/kernels/sim_kernels.cl ("sim.cl") update_e_b_dynamic :897-993, own-LOD loop :940-955.
+//
+// Why: the reference sums, for every cell, over the 8^D sources of its own finest LOD level (4096 at the default depth 4) --
+// 9 multiply-adds per (cell, source) pair even after the Toeplitz tiling of fields.cu, 1.06e12 FMA per step at 256^3, 95 % of
+// the whole time step.  But the sources sit on a regular ND^3 grid (ND = 2^D) and a cell is (block b, in-block offset o):
+//     r = cell - centre = (b - c) * ds + (o - ds/2)            (sim.cl:945-946, lod_coordinates :440-447)
+// so for a FIXED offset o the ND^3 cells that share it see the sources through a kernel that depends on b - c only:
+//     E_o(b) = sum_c K_o(b - c) q(c),    B_o(b) = sum_c w(c) x K_o(b - c),    K_o(d) = r / |r|^3,  w = q v
+// -- a 3-D linear convolution of ND^3 sources with a (2 ND)^3 kernel, one per offset ("polyphase").  With M = 2 ND points per
+// axis the circular convolution has no wrap-around, and the convolution theorem turns 8^D terms per cell into
+// O(log M) work: ~4.5 MFLOP per offset instead of 300 MFLOP.
+//   * K^_o = FFT3(K_o) (Hermitian half spectrum, H = ND + 1 planes along x) is static per geometry: computed once
+//     (eb_khat_*), kept in HBM, 102 B per cell.  The normalisation 1/M^3 and the factor 2 of the Hermitian fold are baked in.
+//   * s^_j = FFT3(q, q vx, q vy, q vz) once per step (eb_src_*), 4 x H x M x M complex, L2 resident.
+//   * per offset (eb_main_*): for each kx plane  E^_c = K^_c s^_0,  B^ = w^ x K^  (9 complex products per frequency),
+//     2-D inverse FFT over (ky, kz) in shared memory, pruned to the ND x ND outputs that exist, and the last axis as a
+//     direct Hermitian DFT accumulation  E(x) += Re e(kx) cos(2 pi kx x / M) - Im e(kx) sin(2 pi kx x / M)  into registers
+//     (17 planes x 16 outputs: cheap, and it removes the third transpose and the 192 KB buffer it would need).
+// Quirks kept: the window [NUM_LOD_OWN - 8^D, NUM_LOD_OWN) with positions taken from the table index (Q5), the self-skip
+// d == lod_index(cell) (sim.cl:944) as K_o(0) = 0, lod_index overflow planes of halo-inclusive slabs (Q7) as extra
+// z windows.  Summation order differs from the reference (as does every parallel sum): E/B agree to ~2e-7 relative L2
+// (tests/test_gpu_parity.py), the deterministic mode keeps the reference's order and arithmetic.
+//
+// Every phase is a plain function of (thread id, block id): eb_fft.cu calls them between __syncthreads(), and
+// tests/tools/eb_fft_emul.cpp runs the same functions thread by thread on the CPU against a direct double-precision sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#ifdef __CUDACC__
+#define ION_HD __host__ __device__ __forceinline__
+#else
+#define ION_HD inline
+#endif
+
+namespace ion {
+namespace ebfft {
+
+struct Geom {
+    uint32_t nx, ny, nz;
+    uint64_t N;
+    uint32_t dsx, dsy, dsz;  // cells per LOD block
+    uint32_t lo, n_lod_own;  // source window [lo, n_lod_own) of sim.cl:943
+    uint32_t cz0;            // z row of the first window entry: lo / ND^2
+    uint32_t dx, dy, dz;     // domain grid (halo test, sim.cl:145-148)
+    float ke, kmu;
+};
+// one polyphase problem: the cells (b*ds + o) with z blocks [ND*wz, ND*wz + ND)
+struct Task {
+    uint16_t ox, oy, oz, wz;
+};
+
+template <int ND> struct Cfg {
+    static constexpr int M = 2 * ND;      // FFT length per axis
+    static constexpr int H = ND + 1;      // Hermitian half: kx = 0..ND
+    static constexpr int ROW = M + 1;     // padded row of the shared-memory planes (bank-conflict-free strided access)
+    static constexpr int T = 256;         // threads of the main kernel (x accumulators live in registers: 6 * XPT per thread)
+    static constexpr int P = ND == 16 ? 4 : 9;  // kx planes per iteration (shared-memory budget)
+    static constexpr int XG = T / (ND * ND);    // thread groups along x in the accumulation phase
+    static constexpr int XPT = ND / XG;         // x outputs per thread
+    static constexpr int PLANE = 6 * M * ROW;   // float2 per kx plane: E^x E^y E^z B^x B^y B^z
+    static constexpr size_t khat_per_task = (size_t)3 * H * M * M;  // float2
+    static constexpr size_t shat_count = (size_t)4 * H * M * M;     // float2
+    static constexpr size_t main_smem = (size_t)P * PLANE * sizeof(float2) + M * sizeof(float2);
+    static constexpr size_t khat_smem = (size_t)H * M * ROW * sizeof(float2);
+    static constexpr size_t src_smem = (size_t)M * ROW * sizeof(float2);
+};
+
+// cos(2 pi k / 32).  A chain of selects, not a table: with k a compile-time constant after unrolling it folds to an immediate
+// (a local constexpr array is materialised on the stack by nvcc and read back with LDL).
+ION_HD constexpr float tw_cos32_q(int k) {  // k = 0..8
+    return k == 0 ? 1.0f
+         : k == 1 ? 9.807852804e-01f
+         : k == 2 ? 9.238795325e-01f
+         : k == 3 ? 8.314696123e-01f
+         : k == 4 ? 7.071067812e-01f
+         : k == 5 ? 5.555702330e-01f
+         : k == 6 ? 3.826834324e-01f
+         : k == 7 ? 1.950903220e-01f
+                  : 0.0f;
+}
+ION_HD constexpr float tw_cos32(int k) {
+    k &= 31;
+    if (k > 16) k = 32 - k;
+    return k > 8 ? -tw_cos32_q(16 - k) : tw_cos32_q(k);
+}
+ION_HD constexpr float tw_sin32(int k) { return tw_cos32(k + 24); }  // sin(t) = cos(t - pi/2)
+
+ION_HD constexpr int bitrev(int i, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; b++) r |= ((i >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+ION_HD constexpr int ilog2(int m) { return m <= 1 ? 0 : 1 + ilog2(m >> 1); }
+
+// In-register radix-2 decimation-in-time FFT of M = 16 or 32 complex points.  INV = false: e^{-2 pi i k n / M};
+// INV = true: e^{+...}, unnormalised.  Everything is unrolled, so all indices and twiddles are compile-time constants;
+// outputs the caller never reads (pruned transforms) and inputs that are literal zeros fold away.
+template <int M, int LEN, bool INV> struct FftStage {  // butterflies of span LEN, after all shorter spans
+    static ION_HD void run(float2 (&a)[M]) {
+        FftStage<M, LEN / 2, INV>::run(a);
+        constexpr int half = LEN / 2, step = 32 / LEN;
+#pragma unroll
+        for (int i = 0; i < M; i += LEN) {
+#pragma unroll
+            for (int k = 0; k < half; k++) {
+                const int ti = k * step;  // twiddle angle in units of 2 pi / 32, 0..15
+                const float2 u = a[i + k], v = a[i + k + half];
+                float2 w;
+                if (ti == 0) {
+                    w = v;
+                } else if (ti == 8) {
+                    w = INV ? make_float2(-v.y, v.x) : make_float2(v.y, -v.x);
+                } else {
+                    const float c = tw_cos32(ti), sn = INV ? tw_sin32(ti) : -tw_sin32(ti);
+                    w = make_float2(fmaf(v.x, c, -(v.y * sn)), fmaf(v.x, sn, v.y * c));
+                }
+                a[i + k] = make_float2(u.x + w.x, u.y + w.y);
+                a[i + k + half] = make_float2(u.x - w.x, u.y - w.y);
+            }
+        }
+    }
+};
+template <int M, bool INV> struct FftStage<M, 1, INV> {
+    static ION_HD void run(float2 (&)[M]) {}
+};
+template <int M, bool INV> ION_HD void fft_reg(float2 (&a)[M]) {
+    constexpr int BITS = ilog2(M);
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        const int j = bitrev(i, BITS);
+        if (i < j) {
+            const float2 t = a[i];
+            a[i] = a[j];
+            a[j] = t;
+        }
+    }
+    FftStage<M, M, INV>::run(a);
+}
+
+ION_HD float2 cmul(float2 a, float2 b) { return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x)); }
+// a*b - c*d
+ION_HD float2 cmul_sub(float2 a, float2 b, float2 c, float2 d) {
+    const float2 p = cmul(a, b), q = cmul(c, d);
+    return make_float2(p.x - q.x, p.y - q.y);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// K^ of one (task, component): grid (ntasks, 3), Cfg::T threads, shared S[H][M][ROW]
+// ------------------------------------------------------------------------------------------------------
+// signed block difference of circular index m
+template <int ND> ION_HD int circ_diff(int m) { return m < ND ? m : m - 2 * ND; }
+
+template <int ND> ION_HD void khat_phase_x(int tid, int nthreads, const Geom& g, const Task t, int comp, float2* S) {
+    typedef Cfg<ND> C;
+    for (int line = tid; line < C::M * C::M; line += nthreads) {
+        const int mz = line / C::M, my = line % C::M;
+        const int ddy = circ_diff<ND>(my);
+        const int ddz = circ_diff<ND>(mz) + ND * (int)t.wz - (int)g.cz0;  // true block difference along z
+        // r = (float)cell - ((float)c * ds + 0.5 ds): small integers and half-integers, exact in any precision (sim.cl:945, :440-447)
+        const double ry = (double)ddy * g.dsy + ((double)t.oy - 0.5 * g.dsy);
+        const double rz = (double)ddz * g.dsz + ((double)t.oz - 0.5 * g.dsz);
+        float2 a[C::M];
+#pragma unroll
+        for (int mx = 0; mx < C::M; mx++) {
+            const int ddx = circ_diff<ND>(mx);
+            const double rx = (double)ddx * g.dsx + ((double)t.ox - 0.5 * g.dsx);
+            const double r2 = rx * rx + ry * ry + rz * rz;
+            double k = 0.0;
+            if (!(ddx == 0 && ddy == 0 && ddz == 0) && r2 > 0.0) {  // the cell's own block contributes nothing (sim.cl:944)
+                const double inv = 1.0 / (r2 * sqrt(r2));
+                k = (comp == 0 ? rx : comp == 1 ? ry : rz) * inv;
+            }
+            a[mx] = make_float2((float)k, 0.0f);
+        }
+        fft_reg<C::M, false>(a);
+#pragma unroll
+        for (int kx = 0; kx < C::H; kx++) S[(kx * C::M + mz) * C::ROW + my] = a[kx];
+    }
+}
+template <int ND> ION_HD void khat_phase_y(int tid, int nthreads, float2* S) {
+    typedef Cfg<ND> C;
+    for (int line = tid; line < C::H * C::M; line += nthreads) {
+        float2* row = S + (size_t)line * C::ROW;  // line = kx * M + mz
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = row[i];
+        fft_reg<C::M, false>(a);
+#pragma unroll
+        for (int i = 0; i < C::M; i++) row[i] = a[i];
+    }
+}
+// layout of K^: [task][comp][kx][kz][ky]
+template <int ND> ION_HD void khat_phase_z(int tid, int nthreads, int task, int comp, const float2* S, float2* khat) {
+    typedef Cfg<ND> C;
+    for (int line = tid; line < C::H * C::M; line += nthreads) {
+        const int kx = line / C::M, ky = line % C::M;
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = S[(kx * C::M + i) * C::ROW + ky];
+        fft_reg<C::M, false>(a);
+        // 1 / M^3 of the inverse transform; planes 1..ND-1 stand for themselves and their conjugates (Hermitian fold)
+        const float scale = (kx == 0 || kx == ND ? 1.0f : 2.0f) / (float)(C::M * C::M * C::M);
+        float2* out = khat + ((size_t)task * 3 + comp) * C::H * C::M * C::M + (size_t)kx * C::M * C::M + ky;
+#pragma unroll
+        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::M] = make_float2(a[kz].x * scale, a[kz].y * scale);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// s^ of the source table: grid (H, 4), any thread count, shared plane[M][ROW].  Component j: q, q vx, q vy, q vz
+// ------------------------------------------------------------------------------------------------------
+template <int ND> ION_HD float src_value(const Geom& g, const float* QU_lod, int j, int cx, int cy, int czp) {
+    const uint32_t d = (uint32_t)cx + (uint32_t)ND * ((uint32_t)cy + (uint32_t)ND * ((uint32_t)czp + g.cz0));
+    if (d < g.lo || d >= g.n_lod_own) return 0.0f;  // outside the window of sim.cl:943
+    const float q = QU_lod[4u * d];
+    return j == 0 ? q : QU_lod[4u * d + (uint32_t)j] * q;
+}
+template <int ND> ION_HD void src_phase_x(int tid, int nthreads, const Geom& g, const float* QU_lod, int kx, int j, float2* plane) {
+    typedef Cfg<ND> C;
+    for (int idx = tid; idx < (ND + 1) * ND; idx += nthreads) {
+        const int czp = idx / ND, cy = idx % ND;
+        float re = 0.0f, im = 0.0f;
+#pragma unroll
+        for (int cx = 0; cx < ND; cx++) {
+            const float v = src_value<ND>(g, QU_lod, j, cx, cy, czp);
+            const int ti = ((kx * cx) % C::M) * (32 / C::M);
+            re = fmaf(v, tw_cos32(ti), re);
+            im = fmaf(v, -tw_sin32(ti), im);
+        }
+        plane[czp * C::ROW + cy] = make_float2(re, im);
+    }
+}
+template <int ND> ION_HD void src_phase_y(int tid, int nthreads, float2* plane) {
+    typedef Cfg<ND> C;
+    for (int czp = tid; czp <= ND; czp += nthreads) {
+        float2* row = plane + czp * C::ROW;
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = i < ND ? row[i] : make_float2(0.0f, 0.0f);
+        fft_reg<C::M, false>(a);
+#pragma unroll
+        for (int i = 0; i < C::M; i++) row[i] = a[i];
+    }
+}
+// layout of s^: [j][kx][kz][ky]
+template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, const float2* plane, float2* shat) {
+    typedef Cfg<ND> C;
+    for (int ky = tid; ky < C::M; ky += nthreads) {
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = i <= ND ? plane[i * C::ROW + ky] : make_float2(0.0f, 0.0f);
+        fft_reg<C::M, false>(a);
+        float2* out = shat + ((size_t)j * C::H + kx) * C::M * C::M + ky;
+#pragma unroll
+        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::M] = a[kz];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// main kernel: grid ntasks, Cfg::T threads, shared W[P][6][M][ROW] float2 | tw[M] float2
+// ------------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+#define ION_LDG2(p) __ldg(p)
+#else
+#define ION_LDG2(p) (*(p))
+#endif
+
+// phase 1: frequency-domain products of planes kx0 .. kx0+np-1.  NSETS = 2 adds a second (kernel, source) pair -- the
+// level D-1 pyramid of the neighbouring domain -- into the same spectra, so one inverse transform serves both.
+template <int ND, int NSETS>
+ION_HD void main_phase_product(int tid, const float2* khat_task, const float2* shat, const float2* khat2_task, const float2* shat2, int kx0,
+                               int np, float2* W) {
+    typedef Cfg<ND> C;
+    constexpr int MM = C::M * C::M;
+    constexpr size_t CS = (size_t)C::H * MM;  // component stride of K^ and s^
+    for (int idx = tid; idx < np * MM; idx += C::T) {
+        const int p = idx / MM, f = idx % MM;  // f = kz * M + ky
+        const size_t gi = (size_t)(kx0 + p) * MM + f;
+        float2 E[3], B[3];
+        {
+            const float2 k0 = ION_LDG2(khat_task + gi), k1 = ION_LDG2(khat_task + CS + gi), k2 = ION_LDG2(khat_task + 2 * CS + gi);
+            const float2 s0 = ION_LDG2(shat + gi), s1 = ION_LDG2(shat + CS + gi), s2 = ION_LDG2(shat + 2 * CS + gi), s3 = ION_LDG2(shat + 3 * CS + gi);
+            E[0] = cmul(k0, s0);
+            E[1] = cmul(k1, s0);
+            E[2] = cmul(k2, s0);
+            B[0] = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
+            B[1] = cmul_sub(s3, k0, s1, k2);
+            B[2] = cmul_sub(s1, k1, s2, k0);
+        }
+        if (NSETS == 2) {
+            const float2 k0 = ION_LDG2(khat2_task + gi), k1 = ION_LDG2(khat2_task + CS + gi), k2 = ION_LDG2(khat2_task + 2 * CS + gi);
+            const float2 s0 = ION_LDG2(shat2 + gi), s1 = ION_LDG2(shat2 + CS + gi), s2 = ION_LDG2(shat2 + 2 * CS + gi), s3 = ION_LDG2(shat2 + 3 * CS + gi);
+            const float2 e0 = cmul(k0, s0), e1 = cmul(k1, s0), e2 = cmul(k2, s0);
+            const float2 b0 = cmul_sub(s2, k2, s3, k1), b1 = cmul_sub(s3, k0, s1, k2), b2 = cmul_sub(s1, k1, s2, k0);
+            E[0].x += e0.x; E[0].y += e0.y; E[1].x += e1.x; E[1].y += e1.y; E[2].x += e2.x; E[2].y += e2.y;
+            B[0].x += b0.x; B[0].y += b0.y; B[1].x += b1.x; B[1].y += b1.y; B[2].x += b2.x; B[2].y += b2.y;
+        }
+        const int kz = f / C::M, ky = f % C::M;
+        float2* w = W + (size_t)p * C::PLANE + kz * C::ROW + ky;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            w[(size_t)c * C::M * C::ROW] = E[c];
+            w[(size_t)(3 + c) * C::M * C::ROW] = B[c];
+        }
+    }
+}
+// phase 2: inverse FFT along kz of every column (p, spectrum, ky); only the ND outputs z that exist are kept (in place)
+template <int ND> ION_HD void main_phase_z(int tid, int np, float2* W) {
+    typedef Cfg<ND> C;
+    for (int idx = tid; idx < np * 6 * C::M; idx += C::T) {
+        const int ps = idx / C::M, ky = idx % C::M;  // ps = p * 6 + spectrum
+        float2* col = W + (size_t)ps * C::M * C::ROW + ky;
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = col[i * C::ROW];
+        fft_reg<C::M, true>(a);
+#pragma unroll
+        for (int i = 0; i < ND; i++) col[i * C::ROW] = a[i];
+    }
+}
+// phase 3: inverse FFT along ky of every row (p, spectrum, z < ND), pruned to y < ND (in place)
+template <int ND> ION_HD void main_phase_y(int tid, int np, float2* W) {
+    typedef Cfg<ND> C;
+    for (int idx = tid; idx < np * 6 * ND; idx += C::T) {
+        const int ps = idx / ND, z = idx % ND;
+        float2* row = W + ((size_t)ps * C::M + z) * C::ROW;
+        float2 a[C::M];
+#pragma unroll
+        for (int i = 0; i < C::M; i++) a[i] = row[i];
+        fft_reg<C::M, true>(a);
+#pragma unroll
+        for (int i = 0; i < ND; i++) row[i] = a[i];
+    }
+}
+// phase 4: the x axis as a direct Hermitian DFT.  Thread = (y, z, x group); acc[6][XPT] stays in registers across the iterations.
+template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, const float2* W, const float2* tw, float (&acc)[6][Cfg<ND>::XPT]) {
+    typedef Cfg<ND> C;
+    constexpr int YZ = ND * ND;
+    const int yz = tid % YZ, xg = tid / YZ;
+    const int y = yz % ND, z = yz / ND;
+    for (int p = 0; p < np; p++) {
+        const int kx = kx0 + p;
+        float2 v[6];
+#pragma unroll
+        for (int s = 0; s < 6; s++) v[s] = W[((size_t)(p * 6 + s) * C::M + z) * C::ROW + y];
+#pragma unroll
+        for (int i = 0; i < C::XPT; i++) {
+            const int x = xg * C::XPT + i;
+            const float2 cs = tw[(kx * x) & (C::M - 1)];
+#pragma unroll
+            for (int s = 0; s < 6; s++) acc[s][i] = fmaf(v[s].x, cs.x, fmaf(-v[s].y, cs.y, acc[s][i]));
+        }
+    }
+}
+// epilogue: sim.cl:986-992 for the cells of this task
+template <int ND>
+ION_HD void main_phase_write(int tid, const Geom& g, const Task t, const uint8_t* flags, const float* E_stat, const float* B_stat, float* E_dyn,
+                             float* B_dyn, const float (&acc)[6][Cfg<ND>::XPT]) {
+    typedef Cfg<ND> C;
+    constexpr int YZ = ND * ND;
+    const int yz = tid % YZ, xg = tid / YZ;
+    const uint32_t y = (uint32_t)(yz % ND) * g.dsy + t.oy;
+    const uint32_t z = ((uint32_t)(yz / ND) + (uint32_t)ND * t.wz) * g.dsz + t.oz;
+    if (z >= g.nz || y >= g.ny) return;
+    const bool halo_yz = ((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u));
+    if (halo_yz) return;
+#pragma unroll
+    for (int i = 0; i < C::XPT; i++) {
+        const uint32_t x = (uint32_t)(xg * C::XPT + i) * g.dsx + t.ox;
+        if (x >= g.nx) continue;
+        if ((g.dx > 1u) & (x == 0u || x >= g.nx - 1u)) continue;  // is_halo, sim.cl:899
+        const uint64_t n = (uint64_t)x + ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+        if ((flags[n] & 0x1Fu) == 0x01u) continue;  // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
+        E_dyn[n] = E_stat[n] + g.ke * acc[0][i];
+        E_dyn[g.N + n] = E_stat[g.N + n] + g.ke * acc[1][i];
+        E_dyn[2ull * g.N + n] = E_stat[2ull * g.N + n] + g.ke * acc[2][i];
+        B_dyn[n] = B_stat[n] + g.kmu * acc[3][i];
+        B_dyn[g.N + n] = B_stat[g.N + n] + g.kmu * acc[4][i];
+        B_dyn[2ull * g.N + n] = B_stat[2ull * g.N + n] + g.kmu * acc[5][i];
+    }
+}
+
+}  // namespace ebfft
+}  // namespace ion

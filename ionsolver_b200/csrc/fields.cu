@@ -528,13 +528,15 @@ template <bool VOL> __device__ __forceinline__ float4 lds128(const float4* p) {
 #endif
 template <int ND, int NC, int BLOCK, bool VOL>
 __global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ KArgs a, const LodSource* __restrict__ foreign,
-                                                                const uint32_t n_foreign, const __grid_constant__ ForeignSet fs) {
+                                                                const uint32_t n_foreign, const __grid_constant__ ForeignSet fs, const uint32_t mode) {
+    // mode bit 0: foreign-domain sources only (the own pyramid was summed by the polyphase FFT kernels of eb_fft.cu);
+    // mode bit 1: add to E_dyn / B_dyn instead of starting from E_stat / B_stat
     static_assert(ND % NC == 0 && NC % 2 == 0, "cells per thread");
     constexpr int PARTS = ND / NC;
     extern __shared__ float4 s_pair[];  // slot t -> {q_t, q_t', wx_t, wx_t'}, {wy_t, wy_t', wz_t, wz_t'}; t' = next source of the row, cyclic
     const uint32_t fine = (uint32_t)ND * ND * ND;
     const uint32_t lo = a.n_lod_own >= fine ? a.n_lod_own - fine : 0u;  // sim.cl:943
-    const uint32_t cnt = a.n_lod_own - lo;
+    const uint32_t cnt = (mode & 1u) ? 0u : a.n_lod_own - lo;
     for (uint32_t k = threadIdx.x; k < cnt; k += BLOCK) {
         const uint32_t d = lo + k;
         const uint32_t dn = (d % ND == ND - 1u) ? d - (ND - 1u) : d + 1u;  // cyclic successor inside the row
@@ -547,7 +549,7 @@ __global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ K
     __syncthreads();
     __shared__ uint8_t s_nz[ND * ND + 2];  // rows without any charge are skipped, see k_update_e_b_tiled
     {
-        const uint32_t r_lo = lo / ND, n_rows = (a.n_lod_own + ND - 1) / ND - r_lo;
+        const uint32_t r_lo = lo / ND, n_rows = (mode & 1u) ? 0u : (a.n_lod_own + ND - 1) / ND - r_lo;
         for (uint32_t r = threadIdx.x; r < n_rows; r += BLOCK) {
             bool nz = false;
             const int d0 = (int)((r_lo + r) * ND) - (int)lo;
@@ -608,7 +610,7 @@ __global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ K
 
     // ---- own LODs (sim.cl:940-955) ----
     const float rx0 = (float)(kbase * dsx + ox) - 0.5f * dsxf;  // r_x of cell kl = 0 against source c = 0
-    const uint32_t row_lo = lo / ND, row_hi = (a.n_lod_own + ND - 1) / ND;
+    const uint32_t row_lo = lo / ND, row_hi = (mode & 1u) ? row_lo : (a.n_lod_own + ND - 1) / ND;
     for (uint32_t row = row_lo; row < row_hi; row++) {
         if (!s_nz[row - row_lo]) continue;  // no charge in this row of LOD blocks
         const uint32_t cy = row % ND, cz = row / ND;
@@ -763,12 +765,14 @@ __global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ K
         const int j = kl / 2;
         const float ex = (kl & 1) ? e2[j][0].y : e2[j][0].x, ey = (kl & 1) ? e2[j][1].y : e2[j][1].x, ez = (kl & 1) ? e2[j][2].y : e2[j][2].x;
         const float bx = (kl & 1) ? b2[j][0].y : b2[j][0].x, by = (kl & 1) ? b2[j][1].y : b2[j][1].x, bz = (kl & 1) ? b2[j][2].y : b2[j][2].x;
-        a.E_dyn[n] = a.E_stat[n] + a.ke * ex;
-        a.E_dyn[N + n] = a.E_stat[N + n] + a.ke * ey;
-        a.E_dyn[2ull * N + n] = a.E_stat[2ull * N + n] + a.ke * ez;
-        a.B_dyn[n] = a.B_stat[n] + a.kmu * bx;
-        a.B_dyn[N + n] = a.B_stat[N + n] + a.kmu * by;
-        a.B_dyn[2ull * N + n] = a.B_stat[2ull * N + n] + a.kmu * bz;
+        const float* Eb = (mode & 2u) ? a.E_dyn : a.E_stat;
+        const float* Bb = (mode & 2u) ? a.B_dyn : a.B_stat;
+        a.E_dyn[n] = Eb[n] + a.ke * ex;
+        a.E_dyn[N + n] = Eb[N + n] + a.ke * ey;
+        a.E_dyn[2ull * N + n] = Eb[2ull * N + n] + a.ke * ez;
+        a.B_dyn[n] = Bb[n] + a.kmu * bx;
+        a.B_dyn[N + n] = Bb[N + n] + a.kmu * by;
+        a.B_dyn[2ull * N + n] = Bb[2ull * N + n] + a.kmu * bz;
     }
 }
 
@@ -903,8 +907,8 @@ static void describe_foreign(const KArgs& a, uint32_t nd, ForeignSet& fs) {
 }
 
 template <int ND, int NC, int BLOCK, bool VOL>
-static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s) {
-    const size_t smem = (size_t)own * 2 * sizeof(float4);
+static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s, uint32_t mode = 0u) {
+    const size_t smem = (mode & 1u) ? 0 : (size_t)own * 2 * sizeof(float4);
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(k_update_e_b_pair<ND, NC, BLOCK, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * fine_bytes(ND)));
         if (e != cudaSuccess) return e;
@@ -913,7 +917,7 @@ static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t ow
     describe_foreign(a, ND, fs);
     const uint32_t threads_per_plane = (a.nx / ND) * (ND / NC) * a.ny;
     const dim3 grid((threads_per_plane + BLOCK - 1) / BLOCK, a.nz);
-    k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own, fs);
+    k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own, fs, mode);
     return cudaGetLastError();
 }
 
@@ -966,6 +970,17 @@ cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_
     if (exact) k_update_e_b<true><<<grid, b, 0, s>>>(a, src, count);
     else k_update_e_b<false><<<grid, b, 0, s>>>(a, src, count);
     return cudaGetLastError();
+}
+// Foreign-domain pyramids only (sim.cl:957-983), added to the E_dyn / B_dyn the polyphase FFT pass (eb_fft.cu) has written.
+cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches) {
+    const uint32_t count = source_count(a.lod_depth, a.n_lod_own, a.dx, a.dy, a.dz, a.di);
+    const uint32_t nd = 1u << a.lod_depth;
+    const uint32_t own = nd * nd * nd;
+    if (count <= own) return cudaSuccess;  // single domain
+    LodSource* src = reinterpret_cast<LodSource*>(scratch_sources);
+    k_build_sources<<<(count + 255u) / 256u, 256, 0, s>>>(a, src, count);
+    *launches += 2;
+    return a.lod_depth == 4u ? launch_pair<16, 16, 256, true>(a, src, own, count, s, 3u) : launch_pair<8, 8, 256, false>(a, src, own, count, s, 3u);
 }
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di) {
     return (size_t)source_count(lod_depth, n_lod_own, dx, dy, dz, di) * sizeof(LodSource);

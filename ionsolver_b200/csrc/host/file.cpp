@@ -182,7 +182,9 @@ Lbm* decode(const std::vector<uint8_t>& buffer, LbmConfig& config, bool referenc
                 if (mhd) d.write(ION_FIELD_Q, lq.data(), d.n * 4);
             }
         }
-        if (mhd) {
+        if (mhd && !reference_compatible && st.at_end()) {
+            // a single-domain MHD file written by the reference's encoder ends here: file.rs:277-303 never writes N_C / N_M
+        } else if (mhd) {
             const uint32_t n_charges = st.next_u32();  // read and discarded (lbm.charges is commented out, file.rs:166)
             for (uint32_t i = 0; i < n_charges; i++) { st.next_u64(); st.next_f32(); }
             const uint32_t n_magnets = st.next_u32();
@@ -197,12 +199,16 @@ Lbm* decode(const std::vector<uint8_t>& buffer, LbmConfig& config, bool referenc
     return lbm;
 }
 
-void write(Lbm& lbm, const std::string& path) {
-    const std::vector<uint8_t> b = encode(lbm, true);
+// Default on-disk mode = FILE_LAYOUT.txt as written (reference_compatible = false): a file written here reloads to the same
+// state for every storage codec, with MHD and with any domain split, and the reference's decoder accepts it too (it gets the
+// N_C = N_M = 0 trailer its own encoder forgets).  Single-domain files written by the reference load as well; only its
+// FP16S / FP16C discriminant swap (file.rs:68-73 vs :199) is NOT reproduced -- bug compatibility is the explicit opt-in.
+void write(Lbm& lbm, const std::string& path, bool reference_compatible) {
+    const std::vector<uint8_t> b = encode(lbm, reference_compatible);
     std::ofstream out(path, std::ios::binary);
     if (!out.write((const char*)b.data(), (std::streamsize)b.size())) throw IonException(ION_ERR_INVALID, "writing went wrong");
 }
-Lbm* read(const std::string& path, LbmConfig& config) { return decode(read_file(path), config, true, {}); }
+Lbm* read(const std::string& path, LbmConfig& config, bool reference_compatible) { return decode(read_file(path), config, reference_compatible, {}); }
 
 // ---------------------------------------------------------------------------------------------------------------
 // JSON (serde_json of LbmConfig, file.rs:310-334)

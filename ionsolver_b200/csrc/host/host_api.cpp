@@ -77,7 +77,8 @@ int wrap_new(Lbm* l, ion_lbm_t** out) {
 #define ION_TRY(body)                                                       \
     try { body; return 0; }                                                 \
     catch (const IonException& e) { return ion::fail(e.code, "%s", e.what()); } \
-    catch (const std::exception& e) { return ion::fail(ION_ERR_INVALID, "%s", e.what()); }
+    catch (const std::exception& e) { return ion::fail(ION_ERR_INVALID, "%s", e.what()); } \
+    catch (...) { return ion::fail(ION_ERR_INVALID, "unknown exception"); }
 #define ION_NEED(l) if (!(l) || !(l)->lbm) return ion::fail(ION_ERR_INVALID, "NULL lbm")
 
 extern "C" {

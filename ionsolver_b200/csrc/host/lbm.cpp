@@ -314,6 +314,11 @@ Lbm* Lbm::create_distributed(LbmConfig cfg, int rank, int world, int device, con
 }
 
 Lbm::~Lbm() {
+    // A partner domain's stream (possibly on another GPU) may still hold a peer copy or an insert kernel that reads this
+    // domain's transfer buffers: drain every stream, halo streams included (ion_finish joins them), before anything is freed.
+    for (auto& d : domains) {
+        if (d.dev) ion_finish(d.dev);  // no throw from a destructor
+    }
     domains.clear();
     if (comm) ion_comm_destroy(comm);
 }
@@ -346,6 +351,17 @@ void Lbm::run(uint64_t steps) {  // mod.rs:235-245
 }
 
 void Lbm::do_time_step() {  // mod.rs:250-272
+    try {
+        do_time_step_body();
+    } catch (...) {
+        // leave no halo stream forked and nothing queued that refers to another domain's buffers before the error propagates
+        for (auto& d : domains)
+            if (d.dev) ion_finish(d.dev);
+        throw;
+    }
+}
+
+void Lbm::do_time_step_body() {
     const bool mhd = config.ext_magneto_hydro;
     if (mhd) clear_qu_lod();
     stream_collide();

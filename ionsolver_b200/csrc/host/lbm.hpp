@@ -200,6 +200,7 @@ struct Lbm {
     void initialize();            // mod.rs:214
     void run(uint64_t steps);     // mod.rs:235
     void do_time_step();          // mod.rs:250
+    void do_time_step_body();
     void finish_queues();         // mod.rs:275
     void precompute_B();          // mod.rs:284
     void precompute_E();          // mod.rs:301
@@ -241,8 +242,8 @@ Lbm* setup_charged_fluid(uint32_t nx, uint32_t ny, uint32_t nz, VelocitySet vs, 
 namespace file {
 std::vector<uint8_t> encode(Lbm& lbm, bool reference_compatible);              // file.rs:191-306
 Lbm* decode(const std::vector<uint8_t>& buffer, LbmConfig& config, bool reference_compatible, const std::vector<int>& devices);  // file.rs:42-188
-void write(Lbm& lbm, const std::string& path);                                  // file.rs:23-31
-Lbm* read(const std::string& path, LbmConfig& config);                         // file.rs:12-20
+void write(Lbm& lbm, const std::string& path, bool reference_compatible = false);  // file.rs:23-31
+Lbm* read(const std::string& path, LbmConfig& config, bool reference_compatible = false);  // file.rs:12-20
 std::string config_to_json(const LbmConfig& cfg);                              // serde_json::to_vec, file.rs:323-334
 LbmConfig config_from_json(const std::string& text);                           // serde_json::from_slice, file.rs:310-321
 void write_config(const std::string& path, const LbmConfig& cfg);

@@ -80,7 +80,9 @@ Mesh Mesh::read_stl_raw(const std::vector<uint8_t>& f, bool reposition, F32_3 bo
     if (f.size() < 84) throw IonException(ION_ERR_INVALID, "Mesh import failed: file shorter than an STL header");
     uint32_t tn;
     memcpy(&tn, &f[80], 4);
-    if (!(tn > 0 && (uint32_t)f.size() == 84u + 50u * tn))  // mesh.rs:179-184
+    // mesh.rs:179-184 compares in 32 bits (and panics on the out-of-bounds read that a wrapped product would cause); here the
+    // comparison is done in 64 bits so that a crafted triangle count cannot pass the check and drive reads past the buffer
+    if (!(tn > 0 && (uint64_t)f.size() == 84ull + 50ull * (uint64_t)tn))
         throw IonException(ION_ERR_INVALID, "Mesh import failed: corrupted or unsupported file (only binary .stl)");
     Mesh mesh;
     mesh.triangle_number = tn;
@@ -89,6 +91,7 @@ Mesh Mesh::read_stl_raw(const std::vector<uint8_t>& f, bool reposition, F32_3 bo
     size_t pos = 84;
     auto next3 = [&]() { float v[3]; memcpy(v, &f[pos], 12); pos += 12; return v3(v[0], v[1], v[2]); };
     for (uint32_t i = 0; i < tn; i++) {
+        if (pos + 50 > f.size()) throw IonException(ION_ERR_RANGE, "Mesh import failed: triangle data past the end of the file");
         pos += 12;  // normal
         mesh.p0[i] = mul(rotation, next3());
         mesh.p1[i] = mul(rotation, next3());

@@ -339,7 +339,7 @@ class Lbm:
         check(self.lib.ion_lbm_setup_velocity_field(self.handle, velocity[0], velocity[1], velocity[2], density))
 
     # ---- file.rs ----
-    def encode(self, reference_compatible=True) -> bytes:
+    def encode(self, reference_compatible=False) -> bytes:
         data, ln = ctypes.c_void_p(), ctypes.c_size_t()
         check(self.lib.ion_lbm_encode(self.handle, int(reference_compatible), ctypes.byref(data), ctypes.byref(ln)))
         try:
@@ -348,7 +348,7 @@ class Lbm:
             self.lib.ion_free(data)
 
     @classmethod
-    def decode(cls, data: bytes, config: LbmConfig = None, reference_compatible=True, devices=None):
+    def decode(cls, data: bytes, config: LbmConfig = None, reference_compatible=False, devices=None):
         c = (config or LbmConfig()).to_c()
         h = ctypes.c_void_p()
         arr, nd = _devs(devices)

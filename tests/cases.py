@@ -93,6 +93,27 @@ def multi_domain_mhd_cases():
                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True), 16.0)),
         ("mhd_z3_d3q19_fp32_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=16, n_z=42, d_z=3, nu=0.05,
                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
+        # the template combinations of BASELINE.json's scaling configurations on block-aligned small lattices:
+        # cfg4 = D3Q27 x FP16S x MHD x z split x depth 4 (D3Q27 with canonical weights, quirk Q3), cfg5 = D3Q19 x FP16C x MHD x z split x depth 4
+        ("mhd_z2_d3q27_fp16s_lod4", _mhd(C(velocity_set="D3Q27", float_type="FP16S", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
+                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 16.0)),
+        ("mhd_z2_d3q19_fp16c_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP16C", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
+                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True), 16.0)),
+    ]
+
+
+def ragged_mhd_cases():
+    """z slabs whose halo-inclusive height is NOT a multiple of 2^depth -- what every benchmark slab looks like (256 + 2 layers):
+    lod_index overflows for the top layers (quirk Q7; the oracle drops deposits past the end of QU_lod), and update_e_b_dynamic
+    has cells whose z block index is 2^depth (an extra z window of the polyphase FFT path).  Default mode only: the
+    deterministic mode needs block-aligned slabs."""
+    return [
+        ("mhd_z2_d3q19_fp32_lod3_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=32, d_z=2, nu=0.05,
+                                                ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=3), 16.0)),
+        ("mhd_z2_d3q19_fp32_lod4_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=16, n_z=64, d_z=2, nu=0.05,
+                                                ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
+        ("mhd_z3_d3q19_fp16s_lod4_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=16, n_y=32, n_z=48, d_z=3, nu=0.05,
+                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
     ]
 
 

@@ -234,7 +234,7 @@ def test_multi_domain_bit_exact(name, cfg, golden, gpu_lib):
     gpu.close()
 
 
-MULTI_MHD = cases.multi_domain_mhd_cases()
+MULTI_MHD = cases.multi_domain_mhd_cases() + cases.ragged_mhd_cases()
 
 
 @pytest.mark.parametrize("name,cfg", MULTI_MHD, ids=[c[0] for c in MULTI_MHD])
@@ -327,12 +327,40 @@ def test_ion_file_round_trip(gpu_lib, tmp_path):
     swapped = L.Lbm.decode(spec, reference_compatible=True, devices=[0])
     assert swapped.config.float_type == L.FloatType.FP16S
     swapped.close()
-    # files
+    # files: write() / read() default to the self-consistent layout (the library reloads what it wrote: MHD, FP16C)
     p = tmp_path / "state.ion"
-    gpu.config.ext_magneto_hydro and None
     gpu.write(p)
-    assert open(p, "rb").read() == blob
+    assert open(p, "rb").read() == spec
+    again = L.Lbm.read(p)
+    assert again.config.float_type == L.FloatType.FP16C and again.config.ext_magneto_hydro
+    for name in ("flags", "rho", "u", "qc"):
+        assert same_bits(again.domains[0].read(cases.FIELD_OF[name]), getattr(rd, name))
+    again.close()
+    # a single-domain MHD file as the reference's own encoder writes it (no N_C / N_M trailer) loads too
+    p2 = tmp_path / "reference_written.ion"
+    open(p2, "wb").write(blob)
+    tolerant = L.Lbm.read(p2)
+    assert same_bits(tolerant.domains[0].read(cases.FIELD_OF["qc"]), rd.qc)
+    tolerant.close()
     gpu.close()
+    # write-then-read round trip with MHD, FP16S and a z split: identical global sections, identical codec
+    cfg_s = cases._mhd(cases.C(velocity_set="D3Q19", float_type="FP16S", n_x=8, n_y=8, n_z=12, d_z=2, nu=0.05, ext_volume_force=True,
+                               ext_magneto_hydro=True, mhd_lod_depth=1), 8.0)
+    ref_s = rh.RefLbm(cfg_s, threads=1, backend="port")
+    cases.fill_inputs(ref_s, cfg_s, seed=9)
+    g_s = product(cfg_s)
+    cases.upload_inputs(ref_s, g_s)
+    p3 = tmp_path / "split.ion"
+    g_s.write(p3)
+    r_s = L.Lbm.read(p3)
+    assert r_s.config.float_type == L.FloatType.FP16S and r_s.get_d_n() == 2
+    assert r_s.encode() == g_s.encode() == open(p3, "rb").read()
+    for da, db in zip(g_s.domains, r_s.domains):
+        ia = da.read(cases.FIELD_OF["qc"]).reshape(da.n_z, da.n_y, da.n_x)[1:-1]
+        ib = db.read(cases.FIELD_OF["qc"]).reshape(db.n_z, db.n_y, db.n_x)[1:-1]
+        assert same_bits(ia, ib)
+    g_s.close()
+    r_s.close()
     # a split lattice saves the same global sections in spec-conformant mode
     cfg1 = cases.C(velocity_set="D3Q19", float_type="FP32", n_x=8, n_y=12, n_z=12, nu=0.05)
     cfg2 = cases.C(velocity_set="D3Q19", float_type="FP32", n_x=8, n_y=12, n_z=12, d_y=2, d_z=3, nu=0.05)
@@ -345,6 +373,27 @@ def test_ion_file_round_trip(gpu_lib, tmp_path):
     assert c.get_d_n() == 6 and c.encode(False) == eb
     for x in (a, b, c):
         x.close()
+
+
+def test_stl_triangle_count_is_checked_in_64_bits(gpu_lib, tmp_path):
+    """mesh.rs:179 compares `84 + 50 * triangles` in 32 bits; a header claiming real + 2^31 triangles wraps to the real file size.
+    The C++ restatement must reject it (the Rust code would panic on the slice bounds instead of reading past the buffer)."""
+    import struct
+    from ionsolver_b200 import capi
+    real = 2
+    body = b"".join(struct.pack("<12fH", *([0.0] * 3 + [float(i), 0, 0, 0, 1.0, 0, 0, 0, 1.0]), 0) for i in range(real))
+    good = b"\0" * 80 + struct.pack("<I", real) + body
+    bad = b"\0" * 80 + struct.pack("<I", real + (1 << 31)) + body
+    assert (84 + 50 * (real + (1 << 31))) % (1 << 32) == len(bad)  # the 32-bit check of mesh.rs:179 would pass
+    pg, pb = tmp_path / "good.stl", tmp_path / "bad.stl"
+    pg.write_bytes(good)
+    pb.write_bytes(bad)
+    gpu = product(cases.C(velocity_set="D3Q19", float_type="FP32", n_x=8, n_y=8, n_z=8, nu=0.05))
+    gpu.import_mesh(str(pg), 1.0, 4.0, 4.0, 4.0, 0.0, 0.0, 0.0)
+    assert gpu.mesh(0)["triangle_number"] == real if "triangle_number" in gpu.mesh(0) else True
+    with pytest.raises(capi.IonError):
+        gpu.import_mesh(str(pb), 1.0, 4.0, 4.0, 4.0, 0.0, 0.0, 0.0)
+    gpu.close()
 
 
 def taylor_green_numpy(n):
