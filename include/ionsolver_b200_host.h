@@ -93,6 +93,12 @@ ION_API int ion_lbm_setup_velocity_field(ion_lbm_t* lbm, float vx, float vy, flo
 ION_API int ion_setup_taylor_green(uint32_t n, uint32_t d_z, int velocity_set, int float_type, int graphics_active, const int* devices,
                                    int n_devices, ion_lbm_t** out);                                    /* setup.rs:92 / :115 */
 ION_API int ion_setup_lid_driven_cavity(uint32_t n, const int* devices, int n_devices, ion_lbm_t** out);
+/* the reference's scene functions by name: "setup_verification" (setup.rs:203), "setup_field_vis" (:244), "setup_ecr_test" (:280),
+ * "setup_mesh_test" (:320), "setup_mesh_field_test" (:346), "setup_deeva_test" (:395), "setup_taylor_green" (:92), "setup_domain_test"
+ * (:115).  stl_dir replaces the hard-coded "stl/" prefix; scale multiplies the lengths of the two mesh scenes (1 = 128 x 256 x 128);
+ * flags for setup_deeva_test: bit 0 = ext_subgrid_ecr as in the reference (off: static E from the plates instead of E_var),
+ * bit 1 = run initialize + the first time step like setup.rs:447-449 */
+ION_API int ion_setup_scene(const char* name, const char* stl_dir, float scale, uint32_t flags, const int* devices, int n_devices, ion_lbm_t** out);
 ION_API int ion_setup_charged_fluid(uint32_t nx, uint32_t ny, uint32_t nz, int velocity_set, int float_type, uint32_t lod_depth,
                                     const char* magnet_stl, const int* devices, int n_devices, ion_lbm_t** out); /* setup.rs:142 + :346 */
 

@@ -58,7 +58,7 @@ HOST_SYMBOLS = [
     "ion_lbm_communicate_qu_lods", "ion_lbm_set_time_step", "ion_lbm_import_mesh", "ion_lbm_import_mesh_reposition",
     "ion_lbm_voxelise_mesh", "ion_lbm_mesh_info", "ion_lbm_mesh_triangles", "ion_lbm_mesh_translate",
     "ion_lbm_set_taylor_green", "ion_lbm_setup_velocity_field", "ion_setup_taylor_green", "ion_setup_lid_driven_cavity",
-    "ion_setup_charged_fluid", "ion_lbm_encode", "ion_lbm_decode", "ion_lbm_write_file", "ion_lbm_read_file",
+    "ion_setup_charged_fluid", "ion_setup_scene", "ion_lbm_encode", "ion_lbm_decode", "ion_lbm_write_file", "ion_lbm_read_file",
     "ion_config_to_json", "ion_config_from_json", "ion_lbm_dump_cell", "ion_lbm_read_slice", "ion_lbm_write_slice_png",
     "ion_iron_colormap", "ion_write_png_rgb", "ion_free",
 ]
@@ -201,6 +201,7 @@ def load() -> ctypes.CDLL:
     L.ion_setup_lid_driven_cavity.argtypes = [c.c_uint32, PI, c.c_int, c.POINTER(H)]
     L.ion_setup_charged_fluid.argtypes = [c.c_uint32, c.c_uint32, c.c_uint32, c.c_int, c.c_int, c.c_uint32, c.c_char_p, PI,
                                           c.c_int, c.POINTER(H)]
+    L.ion_setup_scene.argtypes = [c.c_char_p, c.c_char_p, c.c_float, c.c_uint32, PI, c.c_int, c.POINTER(H)]
     L.ion_lbm_encode.argtypes = [H, c.c_int, c.POINTER(c.c_void_p), c.POINTER(c.c_size_t)]
     L.ion_lbm_decode.argtypes = [c.c_void_p, c.c_size_t, CFG, c.c_int, PI, c.c_int, c.POINTER(H)]
     L.ion_lbm_write_file.argtypes = [H, c.c_char_p]

@@ -46,33 +46,88 @@ template <int ND> __global__ void __launch_bounds__(128) k_eb_src(const __grid_c
     src_phase_z<ND>(threadIdx.x, blockDim.x, kx, j, plane, shat);
 }
 
+// ---- mbarrier + 1-D bulk copy (TMA engine, no registers, no issue slots per byte) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// One block per task.  The K^ slots of the next group of kx planes stream into the idle half of the work buffer (bulk copies
+// armed on an mbarrier by one thread) while the block transforms the current group: the HBM latency of the only large operand
+// is hidden behind the FFT phases, and the products are formed in place where the copy landed.
 template <int ND>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
              const uint8_t* __restrict__ flags, const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
              float* __restrict__ B_dyn) {
     typedef Cfg<ND> C;
-    extern __shared__ __align__(16) unsigned char eb_smem[];
-    float2* W = reinterpret_cast<float2*>(eb_smem);
-    float2* tw = W + (size_t)C::P * C::PLANE;
+    extern __shared__ __align__(128) unsigned char eb_smem[];
+    __shared__ __align__(8) uint64_t bars[2];
+    float2* W = reinterpret_cast<float2*>(eb_smem);  // [2][P][6][M][ROW]
+    float2* tw = W + (size_t)2 * C::P * C::PLANE;
     const int tid = threadIdx.x;
     if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
     const Task t = tasks[blockIdx.x];
     const float2* kt = khat + (size_t)blockIdx.x * C::khat_per_task;
+    if (tid == 0) {
+        mbar_init(&bars[0], 1u);
+        mbar_init(&bars[1], 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto stage = [&](int it) {  // thread 0: K^ of iteration `it` -> E slots, s^_1..3 -> B slots of buffer it & 1
+        const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
+        float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by ordinary loads / stores
+        mbar_expect_tx(&bars[it & 1], (uint32_t)(np * 6 * C::SLOT * sizeof(float2)));
+        for (int p = 0; p < np; p++)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)c * C::SLOT, kt + ((size_t)c * C::H + kx0 + p) * C::SLOT,
+                         (uint32_t)(C::SLOT * sizeof(float2)), &bars[it & 1]);
+                bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT, shat + ((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT,
+                         (uint32_t)(C::SLOT * sizeof(float2)), &bars[it & 1]);
+            }
+    };
+    if (tid == 0) stage(0);
     float acc[6][C::XPT];
 #pragma unroll
     for (int s = 0; s < 6; s++)
 #pragma unroll
         for (int i = 0; i < C::XPT; i++) acc[s][i] = 0.0f;
-    for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
-        const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
-        main_phase_product<ND, 1>(tid, kt, shat, nullptr, nullptr, kx0, np, W);
+    for (int it = 0; it < C::NIT; it++) {
+        const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
+        float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
+        if (tid == 0 && it + 1 < C::NIT) stage(it + 1);  // the other buffer is idle since the barrier that closed iteration it - 1
+        mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
+        main_phase_product<ND>(tid, shat, kx0, np, Wb);
         __syncthreads();
-        main_phase_z<ND>(tid, np, W);
+        main_phase_z<ND>(tid, np, Wb);
         __syncthreads();
-        main_phase_y<ND>(tid, np, W);
+        main_phase_y<ND>(tid, np, Wb);
         __syncthreads();
-        main_phase_accumulate<ND>(tid, kx0, np, W, tw, acc);
+        main_phase_accumulate<ND>(tid, kx0, np, Wb, tw, acc);
         __syncthreads();
     }
     main_phase_write<ND>(tid, g, t, flags, E_stat, B_stat, E_dyn, B_dyn, acc);

@@ -58,13 +58,15 @@ template <int ND> struct Cfg {
     static constexpr int H = ND + 1;      // Hermitian half: kx = 0..ND
     static constexpr int ROW = M + 1;     // padded row of the shared-memory planes (bank-conflict-free strided access)
     static constexpr int T = 256;         // threads of the main kernel (x accumulators live in registers: 6 * XPT per thread)
-    static constexpr int P = ND == 16 ? 4 : 9;  // kx planes per iteration (shared-memory budget)
+    static constexpr int P = ND == 16 ? 2 : 3;  // kx planes per iteration; the kernel holds two such groups (double buffer)
+    static constexpr int NIT = (H + P - 1) / P; // iterations per task
     static constexpr int XG = T / (ND * ND);    // thread groups along x in the accumulation phase
     static constexpr int XPT = ND / XG;         // x outputs per thread
     static constexpr int PLANE = 6 * M * ROW;   // float2 per kx plane: E^x E^y E^z B^x B^y B^z
-    static constexpr size_t khat_per_task = (size_t)3 * H * M * M;  // float2
-    static constexpr size_t shat_count = (size_t)4 * H * M * M;     // float2
-    static constexpr size_t main_smem = (size_t)P * PLANE * sizeof(float2) + M * sizeof(float2);
+    static constexpr int SLOT = M * ROW;        // float2 per (spectrum, kx) slot; K^ and s^ use the same padded rows in HBM
+    static constexpr size_t khat_per_task = (size_t)3 * H * SLOT;  // float2
+    static constexpr size_t shat_count = (size_t)4 * H * SLOT;     // float2
+    static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + M * sizeof(float2);
     static constexpr size_t khat_smem = (size_t)H * M * ROW * sizeof(float2);
     static constexpr size_t src_smem = (size_t)M * ROW * sizeof(float2);
 };
@@ -193,7 +195,8 @@ template <int ND> ION_HD void khat_phase_y(int tid, int nthreads, float2* S) {
         for (int i = 0; i < C::M; i++) row[i] = a[i];
     }
 }
-// layout of K^: [task][comp][kx][kz][ky]
+// layout of K^: [task][comp][kx][kz][ROW] -- rows padded exactly like the shared-memory planes, so that one slot is ONE
+// contiguous bulk copy (cp.async.bulk) into the place where the products are formed
 template <int ND> ION_HD void khat_phase_z(int tid, int nthreads, int task, int comp, const float2* S, float2* khat) {
     typedef Cfg<ND> C;
     for (int line = tid; line < C::H * C::M; line += nthreads) {
@@ -204,9 +207,13 @@ template <int ND> ION_HD void khat_phase_z(int tid, int nthreads, int task, int 
         fft_reg<C::M, false>(a);
         // 1 / M^3 of the inverse transform; planes 1..ND-1 stand for themselves and their conjugates (Hermitian fold)
         const float scale = (kx == 0 || kx == ND ? 1.0f : 2.0f) / (float)(C::M * C::M * C::M);
-        float2* out = khat + ((size_t)task * 3 + comp) * C::H * C::M * C::M + (size_t)kx * C::M * C::M + ky;
+        float2* out = khat + ((size_t)task * 3 + comp) * C::H * C::SLOT + (size_t)kx * C::SLOT + ky;
 #pragma unroll
-        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::M] = make_float2(a[kz].x * scale, a[kz].y * scale);
+        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::ROW] = make_float2(a[kz].x * scale, a[kz].y * scale);
+        if (ky == 0) {  // the padding column is copied along with the rows: keep it defined
+#pragma unroll
+            for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::ROW + C::M] = make_float2(0.0f, 0.0f);
+        }
     }
 }
 
@@ -246,7 +253,7 @@ template <int ND> ION_HD void src_phase_y(int tid, int nthreads, float2* plane) 
         for (int i = 0; i < C::M; i++) row[i] = a[i];
     }
 }
-// layout of s^: [j][kx][kz][ky]
+// layout of s^: [j][kx][kz][ROW] (same padded rows as K^)
 template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, const float2* plane, float2* shat) {
     typedef Cfg<ND> C;
     for (int ky = tid; ky < C::M; ky += nthreads) {
@@ -254,9 +261,9 @@ template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, 
 #pragma unroll
         for (int i = 0; i < C::M; i++) a[i] = i <= ND ? plane[i * C::ROW + ky] : make_float2(0.0f, 0.0f);
         fft_reg<C::M, false>(a);
-        float2* out = shat + ((size_t)j * C::H + kx) * C::M * C::M + ky;
+        float2* out = shat + ((size_t)j * C::H + kx) * C::SLOT + ky;
 #pragma unroll
-        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::M] = a[kz];
+        for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::ROW] = a[kz];
     }
 }
 
@@ -269,43 +276,37 @@ template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, 
 #define ION_LDG2(p) (*(p))
 #endif
 
-// phase 1: frequency-domain products of planes kx0 .. kx0+np-1.  NSETS = 2 adds a second (kernel, source) pair -- the
-// level D-1 pyramid of the neighbouring domain -- into the same spectra, so one inverse transform serves both.
-template <int ND, int NSETS>
-ION_HD void main_phase_product(int tid, const float2* khat_task, const float2* shat, const float2* khat2_task, const float2* shat2, int kx0,
-                               int np, float2* W) {
+// phase 0 (CPU emulation of what the kernel does with cp.async.bulk): the K^ slots of planes kx0 .. kx0+np-1 land in the E
+// slots (0..2) of the work buffer and the s^_1..3 slots (q vx, q vy, q vz) in the B slots (3..5)
+template <int ND> inline void main_stage_host(const float2* khat_task, const float2* shat, int kx0, int np, float2* W) {
+    typedef Cfg<ND> C;
+    for (int p = 0; p < np; p++)
+        for (int c = 0; c < 3; c++)
+            for (int i = 0; i < C::SLOT; i++) {
+                W[(size_t)p * C::PLANE + (size_t)c * C::SLOT + i] = khat_task[((size_t)c * C::H + kx0 + p) * C::SLOT + i];
+                W[(size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT + i] = shat[((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT + i];
+            }
+}
+// phase 1: frequency-domain products of planes kx0 .. kx0+np-1, IN PLACE: the point's K^ (E slots) and s^_1..3 (B slots) are
+// read from where the bulk copies put them, s^_0 comes from L2, and the six products overwrite the same point of the six slots.
+template <int ND> ION_HD void main_phase_product(int tid, const float2* shat, int kx0, int np, float2* W) {
     typedef Cfg<ND> C;
     constexpr int MM = C::M * C::M;
-    constexpr size_t CS = (size_t)C::H * MM;  // component stride of K^ and s^
+#pragma unroll 8
     for (int idx = tid; idx < np * MM; idx += C::T) {
-        const int p = idx / MM, f = idx % MM;  // f = kz * M + ky
-        const size_t gi = (size_t)(kx0 + p) * MM + f;
-        float2 E[3], B[3];
-        {
-            const float2 k0 = ION_LDG2(khat_task + gi), k1 = ION_LDG2(khat_task + CS + gi), k2 = ION_LDG2(khat_task + 2 * CS + gi);
-            const float2 s0 = ION_LDG2(shat + gi), s1 = ION_LDG2(shat + CS + gi), s2 = ION_LDG2(shat + 2 * CS + gi), s3 = ION_LDG2(shat + 3 * CS + gi);
-            E[0] = cmul(k0, s0);
-            E[1] = cmul(k1, s0);
-            E[2] = cmul(k2, s0);
-            B[0] = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
-            B[1] = cmul_sub(s3, k0, s1, k2);
-            B[2] = cmul_sub(s1, k1, s2, k0);
-        }
-        if (NSETS == 2) {
-            const float2 k0 = ION_LDG2(khat2_task + gi), k1 = ION_LDG2(khat2_task + CS + gi), k2 = ION_LDG2(khat2_task + 2 * CS + gi);
-            const float2 s0 = ION_LDG2(shat2 + gi), s1 = ION_LDG2(shat2 + CS + gi), s2 = ION_LDG2(shat2 + 2 * CS + gi), s3 = ION_LDG2(shat2 + 3 * CS + gi);
-            const float2 e0 = cmul(k0, s0), e1 = cmul(k1, s0), e2 = cmul(k2, s0);
-            const float2 b0 = cmul_sub(s2, k2, s3, k1), b1 = cmul_sub(s3, k0, s1, k2), b2 = cmul_sub(s1, k1, s2, k0);
-            E[0].x += e0.x; E[0].y += e0.y; E[1].x += e1.x; E[1].y += e1.y; E[2].x += e2.x; E[2].y += e2.y;
-            B[0].x += b0.x; B[0].y += b0.y; B[1].x += b1.x; B[1].y += b1.y; B[2].x += b2.x; B[2].y += b2.y;
-        }
+        const int p = idx / MM, f = idx % MM;
         const int kz = f / C::M, ky = f % C::M;
-        float2* w = W + (size_t)p * C::PLANE + kz * C::ROW + ky;
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            w[(size_t)c * C::M * C::ROW] = E[c];
-            w[(size_t)(3 + c) * C::M * C::ROW] = B[c];
-        }
+        const int o = kz * C::ROW + ky;
+        float2* w = W + (size_t)p * C::PLANE + o;
+        const float2 s0 = ION_LDG2(shat + (size_t)(kx0 + p) * C::SLOT + o);
+        const float2 k0 = w[0], k1 = w[C::SLOT], k2 = w[2 * C::SLOT];
+        const float2 s1 = w[3 * C::SLOT], s2 = w[4 * C::SLOT], s3 = w[5 * C::SLOT];
+        w[0] = cmul(k0, s0);
+        w[C::SLOT] = cmul(k1, s0);
+        w[2 * C::SLOT] = cmul(k2, s0);
+        w[3 * C::SLOT] = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
+        w[4 * C::SLOT] = cmul_sub(s3, k0, s1, k2);
+        w[5 * C::SLOT] = cmul_sub(s1, k1, s2, k0);
     }
 }
 // phase 2: inverse FFT along kz of every column (p, spectrum, ky); only the ND outputs z that exist are kept (in place)
@@ -356,31 +357,53 @@ template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, co
         }
     }
 }
-// epilogue: sim.cl:986-992 for the cells of this task
+// epilogue: sim.cl:986-992 for the cells of this task.  The cells of one task are ds apart, so every access is its own sector;
+// all loads of a group of x positions (flags, static fields) are issued before anything depends on them -- a loop that tests the
+// flag byte first and then loads costs two dependent HBM round trips per cell (it was 57 % of the kernel's stall samples).
 template <int ND>
 ION_HD void main_phase_write(int tid, const Geom& g, const Task t, const uint8_t* flags, const float* E_stat, const float* B_stat, float* E_dyn,
                              float* B_dyn, const float (&acc)[6][Cfg<ND>::XPT]) {
     typedef Cfg<ND> C;
     constexpr int YZ = ND * ND;
+    constexpr int G = C::XPT < 4 ? C::XPT : 4;  // x positions per group
     const int yz = tid % YZ, xg = tid / YZ;
     const uint32_t y = (uint32_t)(yz % ND) * g.dsy + t.oy;
     const uint32_t z = ((uint32_t)(yz / ND) + (uint32_t)ND * t.wz) * g.dsz + t.oz;
     if (z >= g.nz || y >= g.ny) return;
     const bool halo_yz = ((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u));
     if (halo_yz) return;
+    const uint64_t row = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
 #pragma unroll
-    for (int i = 0; i < C::XPT; i++) {
-        const uint32_t x = (uint32_t)(xg * C::XPT + i) * g.dsx + t.ox;
-        if (x >= g.nx) continue;
-        if ((g.dx > 1u) & (x == 0u || x >= g.nx - 1u)) continue;  // is_halo, sim.cl:899
-        const uint64_t n = (uint64_t)x + ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
-        if ((flags[n] & 0x1Fu) == 0x01u) continue;  // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
-        E_dyn[n] = E_stat[n] + g.ke * acc[0][i];
-        E_dyn[g.N + n] = E_stat[g.N + n] + g.ke * acc[1][i];
-        E_dyn[2ull * g.N + n] = E_stat[2ull * g.N + n] + g.ke * acc[2][i];
-        B_dyn[n] = B_stat[n] + g.kmu * acc[3][i];
-        B_dyn[g.N + n] = B_stat[g.N + n] + g.kmu * acc[4][i];
-        B_dyn[2ull * g.N + n] = B_stat[2ull * g.N + n] + g.kmu * acc[5][i];
+    for (int i0 = 0; i0 < C::XPT; i0 += G) {
+        uint64_t n[G];
+        bool live[G];
+        uint8_t fl[G];
+        float st[6][G];
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const uint32_t x = (uint32_t)(xg * C::XPT + i0 + k) * g.dsx + t.ox;
+            live[k] = x < g.nx && !((g.dx > 1u) & (x == 0u || x >= g.nx - 1u));  // is_halo, sim.cl:899
+            n[k] = row + (live[k] ? x : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < G; k++) fl[k] = flags[n[k]];
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                st[c][k] = E_stat[(uint64_t)c * g.N + n[k]];
+                st[3 + c][k] = B_stat[(uint64_t)c * g.N + n[k]];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            if (!live[k] || (fl[k] & 0x1Fu) == 0x01u) continue;  // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                E_dyn[(uint64_t)c * g.N + n[k]] = st[c][k] + g.ke * acc[c][i0 + k];
+                B_dyn[(uint64_t)c * g.N + n[k]] = st[3 + c][k] + g.kmu * acc[3 + c][i0 + k];
+            }
+        }
     }
 }
 

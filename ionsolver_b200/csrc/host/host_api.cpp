@@ -253,6 +253,12 @@ int ion_setup_charged_fluid(uint32_t nx, uint32_t ny, uint32_t nz, int vs, int f
     ION_TRY(wrap_new(setup_charged_fluid(nx, ny, nz, (VelocitySet)vs, (FloatType)ft, (uint8_t)lod_depth, magnet_stl ? magnet_stl : "", devs(devices, n_devices)), out))
 }
 
+int ion_setup_scene(const char* name, const char* stl_dir, float scale, uint32_t flags, const int* devices, int n_devices, ion_lbm_t** out) {
+    if (!out || !name) return ion::fail(ION_ERR_INVALID, "NULL argument");
+    *out = nullptr;
+    ION_TRY(wrap_new(setup_scene(name, stl_dir ? stl_dir : "stl", scale, flags, devs(devices, n_devices)), out))
+}
+
 int ion_lbm_encode(ion_lbm_t* l, int reference_compatible, uint8_t** data, size_t* len) {
     ION_NEED(l);
     if (!data || !len) return ion::fail(ION_ERR_INVALID, "NULL out");

@@ -238,6 +238,15 @@ Lbm* setup_lid_driven_cavity(uint32_t n, const std::vector<int>& devices);      
 Lbm* setup_charged_fluid(uint32_t nx, uint32_t ny, uint32_t nz, VelocitySet vs, FloatType ft, uint8_t lod_depth,
                          const std::string& magnet_stl, const std::vector<int>& devices);        // cfg2: setup.rs:142-201 + :346-393
 
+// the reference's other scene functions (setup.rs:203-453), see setup.cpp
+Lbm* setup_verification(const std::vector<int>& devices);                                         // setup.rs:203-241
+Lbm* setup_field_vis(const std::vector<int>& devices);                                            // setup.rs:244-277
+Lbm* setup_ecr_test(const std::vector<int>& devices);                                             // setup.rs:280-317
+Lbm* setup_mesh_test(const std::string& stl_dir, const std::vector<int>& devices);                // setup.rs:320-343
+Lbm* setup_mesh_field_test(const std::string& stl_dir, float scale, const std::vector<int>& devices);  // setup.rs:346-393
+Lbm* setup_deeva_test(const std::string& stl_dir, float scale, bool subgrid_ecr, bool first_step, const std::vector<int>& devices);  // setup.rs:395-453
+Lbm* setup_scene(const std::string& name, const std::string& stl_dir, float scale, uint32_t flags, const std::vector<int>& devices);  // setup.rs:22-64
+
 // ---- file.rs ---------------------------------------------------------------------------------------------------
 namespace file {
 std::vector<uint8_t> encode(Lbm& lbm, bool reference_compatible);              // file.rs:191-306

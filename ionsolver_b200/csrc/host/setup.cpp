@@ -139,4 +139,173 @@ Lbm* setup_charged_fluid(uint32_t nx, uint32_t ny, uint32_t nz, VelocitySet vs, 
     return lbm;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The reference's remaining scene functions (setup.rs), selectable by name.  Each keeps the reference's units, sizes, mesh
+// placements and model types; what belongs to the rasteriser (camera, colours, streamline settings) has no effect on the path.
+// `stl_dir` replaces the hard-coded "stl/" prefix.  `scale` multiplies all lengths of the two mesh scenes (1 = the reference's
+// 128 x 256 x 128; BASELINE cfg3 uses 2); `subgrid_ecr` overrides setup_deeva_test's ext_subgrid_ecr = true, which overflows
+// within two steps in the reference itself -- pass false for runs, true for the literal scene.
+// ---------------------------------------------------------------------------------------------------------------
+static bool file_exists(const std::string& p) {
+    FILE* f = fopen(p.c_str(), "rb");
+    if (f) fclose(f);
+    return f != nullptr;
+}
+
+Lbm* setup_verification(const std::vector<int>& devices) {  // setup.rs:203-241: 1 C moving at 1 m/s in cell 0
+    LbmConfig cfg;
+    cfg.units.set(1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 0.5f, 1.0f, 1.0f, 10.0f, 1.0f);
+    cfg.n_x = cfg.n_y = cfg.n_z = 128;
+    cfg.nu = cfg.units.nu_si_lu(1.48E-5f);
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.mhd_lod_depth = 4;
+    cfg.ext_volume_force = true;
+    cfg.ext_magneto_hydro = true;
+    cfg.graphics_config.graphics_active = true;
+    Lbm* lbm = Lbm::create(cfg, devices);
+    const uint64_t N = (uint64_t)cfg.n_x * cfg.n_y * cfg.n_z;
+    std::vector<float> charge(N, 0.0f), vel(3 * N, 0.0f), rho(N, 1.0f);
+    charge[0] = 1.0f;
+    vel[0] = 1.0f;
+    lbm->domains[0].write(ION_FIELD_Q, charge.data(), N * 4);
+    lbm->domains[0].write(ION_FIELD_U, vel.data(), 3 * N * 4);
+    lbm->domains[0].write(ION_FIELD_RHO, rho.data(), N * 4);
+    return lbm;
+}
+
+Lbm* setup_field_vis(const std::vector<int>& devices) {  // setup.rs:244-277 (its magnets are commented out in the reference)
+    LbmConfig cfg;
+    cfg.units.set(128.0f, 1.0f, 1.0f, 1.0f, 1.0f, 0.1f, 1.0f, 1.2250f, 0.0000000001f, 1.0f);
+    cfg.n_x = cfg.n_y = cfg.n_z = 256;
+    cfg.nu = cfg.units.nu_si_lu(1.48E-5f);
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.mhd_lod_depth = 4;
+    cfg.ext_volume_force = true;
+    cfg.ext_magneto_hydro = true;
+    cfg.graphics_config.graphics_active = true;
+    return Lbm::create(cfg, devices);
+}
+
+Lbm* setup_ecr_test(const std::vector<int>& devices) {  // setup.rs:280-317
+    LbmConfig cfg;
+    cfg.units.set(1.0f, 1.0f, 1.0f, 1.0f, 1.0f, 0.01f, 10000.0f, 10E-8f, 0.0000000000001f, 50000.0f);
+    cfg.n_x = cfg.n_y = cfg.n_z = 10;
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.ext_volume_force = true;
+    cfg.ext_magneto_hydro = true;
+    cfg.ecr_freq = cfg.units.time_lu_si(2.45E9f);
+    cfg.mhd_lod_depth = 1;
+    Lbm* lbm = Lbm::create(cfg, devices);
+    std::vector<float> b(3000, 0.0f);
+    const float by = cfg.units.mag_flux_si_lu(0.0875f);
+    for (int i = 1000; i < 2000; i++) b[i] = by;
+    lbm->domains[0].write(ION_FIELD_B_STAT, b.data(), b.size() * 4);
+    return lbm;
+}
+
+Lbm* setup_mesh_test(const std::string& stl_dir, const std::vector<int>& devices) {  // setup.rs:320-343
+    LbmConfig cfg;
+    cfg.n_x = 128; cfg.n_y = 256; cfg.n_z = 128;
+    cfg.nu = cfg.units.nu_si_lu(0.05f);
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.graphics_config.graphics_active = true;
+    Lbm* lbm = Lbm::create(cfg, devices);
+    try {
+        size_t next = 0;
+        // stl/cow.stl is git-ignored in the reference (.gitignore:1) and absent from most checkouts: optional here
+        if (file_exists(stl_dir + "/cow.stl")) {
+            lbm->import_mesh_reposition(stl_dir + "/cow.stl", 64.0f, 128.0f, 64.0f, 0.0f, 0.0f, 0.0f, 200.0f);
+            F32_3 off;
+            off.z = 128.0f - lbm->meshes[0].p_max.z;
+            lbm->meshes[0].translate(off);
+            lbm->voxelise_mesh(next++, ModelType::solid());
+        }
+        lbm->import_mesh_reposition(stl_dir + "/ring-magnet.stl", 64.5f, 10.0f, 64.0f, 0.0f, 0.0f, 0.0f, 127.0f);
+        lbm->voxelise_mesh(next, ModelType::magnet(0.0f, 0.0f, 0.0f));
+    } catch (...) {
+        delete lbm;
+        throw;
+    }
+    return lbm;
+}
+
+Lbm* setup_mesh_field_test(const std::string& stl_dir, float scale, const std::vector<int>& devices) {  // setup.rs:346-393
+    LbmConfig cfg;
+    cfg.units.set(128.0f * scale, 1.0f, 1.0f, 1.0f, 1.0f, 0.1f, 1.0f, 1.2250f, 0.0000000001f, 1.0f);
+    cfg.n_x = (uint32_t)(128.0f * scale); cfg.n_y = (uint32_t)(256.0f * scale); cfg.n_z = (uint32_t)(128.0f * scale);
+    cfg.nu = cfg.units.nu_si_lu(0.05f);
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.ecr_freq = cfg.units.time_lu_si(2.45E9f);
+    cfg.ext_volume_force = true;
+    cfg.ext_magneto_hydro = true;
+    cfg.graphics_config.graphics_active = true;
+    Lbm* lbm = Lbm::create(cfg, devices);
+    try {
+        lbm->import_mesh_reposition(stl_dir + "/disk-magnet.stl", 64.1f * scale, 246.1f * scale, 64.0f * scale, 0.0f, 0.0f, 0.0f, 127.0f * scale);
+        lbm->import_mesh(stl_dir + "/ring-magnet.stl", 1.0f, 64.1f * scale, 64.1f * scale, 64.0f * scale, 0.0f, 0.0f, 0.0f);
+        lbm->voxelise_mesh(0, ModelType::magnet(0.0f, 1000000.0f, 0.0f));
+        lbm->voxelise_mesh(1, ModelType::magnet(0.0f, 1000000.0f, 0.0f));
+        // lbm.precompute_B() is commented out in the reference (setup.rs:388)
+    } catch (...) {
+        delete lbm;
+        throw;
+    }
+    return lbm;
+}
+
+Lbm* setup_deeva_test(const std::string& stl_dir, float scale, bool subgrid_ecr, bool first_step, const std::vector<int>& devices) {  // setup.rs:395-453
+    LbmConfig cfg;
+    cfg.units.set(128.0f * scale, 1.0f, 1.0f, 1.0f, 1.0f, 0.1f, 1.0f, 10e-8f, 1.0f, 50000.0f);
+    cfg.n_x = (uint32_t)(128.0f * scale); cfg.n_y = (uint32_t)(256.0f * scale); cfg.n_z = (uint32_t)(128.0f * scale);
+    cfg.nu = cfg.units.nu_si_lu(0.05f);
+    cfg.velocity_set = VelocitySet::D3Q19;
+    cfg.ecr_freq = cfg.units.time_lu_si(2.45E9f);
+    cfg.ext_volume_force = true;
+    cfg.ext_magneto_hydro = true;
+    cfg.ext_subgrid_ecr = subgrid_ecr;
+    cfg.graphics_config.graphics_active = true;
+    Lbm* lbm = Lbm::create(cfg, devices);
+    try {
+        const float c = 64.0f * scale;
+        lbm->import_mesh(stl_dir + "/deeva_disk_magnet.stl", 1.0f, 64.001f * scale, 0.0f, c, 0.0f, 0.0f, 0.0f);
+        lbm->import_mesh(stl_dir + "/deeva_inlet.stl", 1.0f, c, 0.0f, c, 0.0f, 0.0f, 0.0f);
+        lbm->import_mesh(stl_dir + "/deeva_quartz_tube.stl", 1.0f, 64.001f * scale, 0.0f, c, 0.0f, 0.0f, 0.0f);
+        lbm->import_mesh(stl_dir + "/deeva_ring_magnet.stl", 1.0f, 64.001f * scale, -0.5f * scale, c, 0.0f, 0.0f, 0.0f);
+        lbm->import_mesh(stl_dir + "/deeva_e_plate1.stl", 1.0f, c, 0.0f, c, 0.0f, 0.0f, 0.0f);
+        lbm->import_mesh(stl_dir + "/deeva_e_plate2.stl", 1.0f, c, 0.0f, c, 0.0f, 0.0f, 0.0f);
+        lbm->voxelise_mesh(0, ModelType::magnet(0.0f, 1000000.0f, 0.0f));
+        lbm->voxelise_mesh(1, ModelType::solid());
+        lbm->voxelise_mesh(2, ModelType::solid());
+        lbm->voxelise_mesh(3, ModelType::magnet(0.0f, 500000.0f, 0.0f));
+        // 2000 V over 0.05 m, 0.0015 m^2: Q = C V = 5.3e-10 C over 2432 plate cells (setup.rs:433-440)
+        lbm->voxelise_mesh(4, ModelType::charged_ecr(0.00000000000021844213f / 2.0f));
+        lbm->voxelise_mesh(5, ModelType::charged_ecr(-0.00000000000021844213f / 2.0f));
+        lbm->precompute_B();
+        if (subgrid_ecr) lbm->precompute_E_ECR();  // E_var only exists with ext_subgrid_ecr (domain.rs:200-211)
+        else lbm->precompute_E();                   // "static E from plates" for BASELINE cfg3
+        if (first_step) {
+            lbm->initialize();
+            lbm->do_time_step();
+        }
+    } catch (...) {
+        delete lbm;
+        throw;
+    }
+    return lbm;
+}
+
+// dispatch by the reference's function name
+Lbm* setup_scene(const std::string& name, const std::string& stl_dir, float scale, uint32_t flags, const std::vector<int>& devices) {
+    if (!(scale > 0.0f)) scale = 1.0f;
+    if (name == "setup_verification") return setup_verification(devices);
+    if (name == "setup_field_vis") return setup_field_vis(devices);
+    if (name == "setup_ecr_test") return setup_ecr_test(devices);
+    if (name == "setup_mesh_test") return setup_mesh_test(stl_dir, devices);
+    if (name == "setup_mesh_field_test") return setup_mesh_field_test(stl_dir, scale, devices);
+    if (name == "setup_deeva_test") return setup_deeva_test(stl_dir, scale, (flags & 1u) != 0, (flags & 2u) != 0, devices);
+    if (name == "setup_taylor_green") return setup_taylor_green(256, 1, VelocitySet::D3Q19, FloatType::FP16S, true, devices);  // setup.rs:92-113
+    if (name == "setup_domain_test") return setup_taylor_green(256, 2, VelocitySet::D3Q19, FloatType::FP16S, true, devices);   // setup.rs:115-139
+    throw IonException(ION_ERR_INVALID, "unknown scene \"" + name + "\" (setup.rs:22-64)");
+}
+
 }  // namespace ionhost

@@ -20,74 +20,122 @@ __device__ __forceinline__ float3 cross3(float3 a, float3 b) {
     return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 __device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__host__ __device__ __forceinline__ int clampi(int x, int lo, int hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
-// voxelize_mesh, sim.cl:1150-1231: one thread per column of the face perpendicular to `direction`
-__global__ void k_voxelize(const __grid_constant__ KArgs a, const uint32_t direction, const uint8_t flag, const float* __restrict__ p0,
-                           const float* __restrict__ p1, const float* __restrict__ p2, const uint32_t triangle_number, const float x0,
-                           const float y0, const float z0, const float x1, const float y1, const float z1, const float mpc_x,
-                           const float mpc_y, const float mpc_z, const int mhd) {
-    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+// ------------------------------------------------------------------------------------------------------
+// voxelize_mesh (behaviour: sim.cl:1150-1231; host side mesh.rs:281-343).  One thread per column of the face perpendicular
+// to the ray direction, organised for the GPU rather than after the reference's loop:
+//   * everything of the ray-triangle test that does not depend on the column -- the edges u = p1-p0, v = p2-p0, h = dir x v and
+//     f = 1/(u.h) -- is computed ONCE per triangle by the block and kept in shared memory (64-byte records, broadcast reads);
+//     a column only evaluates w = origin - p0, s = f (w.h), q = w x u, t = f q_dir, d = f (v.q).  The expressions and their
+//     operation order are the reference's (Moeller-Trumbore), so s, t, d -- and with them the flags -- are bit-identical.
+//   * the hit distances are not kept as a sorted list: a hit toggles bit floor(d) of a per-column bitmap in shared memory.
+//     The reference's fill loop only ever asks "how many of the (first 64) hits lie strictly below this cell", and only for the
+//     PARITY of that count; walking up the column, the running XOR of the bitmap is that parity.  Its error-correction rules
+//     reduce to closed forms: start index k0 = [hits ahead and behind differ in parity] skips the nearest hit (toggles
+//     = max(k0, cnt) - k0), and nothing is inside at or beyond the farthest stored hit (hmesh).  No sort, no per-thread array.
+// ------------------------------------------------------------------------------------------------------
+struct __align__(16) TriRecord {
+    float p0x, p0y, p0z, f;
+    float ux, uy, uz, hx;
+    float vx, vy, vz, hy;
+    float hz, pad0, pad1, pad2;
+};
+constexpr int VOX_BLOCK = 128;
+constexpr int VOX_CHUNK = 256;  // triangle records per shared-memory stage
+
+__global__ void __launch_bounds__(VOX_BLOCK) k_voxelize(const __grid_constant__ KArgs a, const uint32_t direction, const uint8_t flag,
+                                                         const float* __restrict__ p0, const float* __restrict__ p1, const float* __restrict__ p2,
+                                                         const uint32_t triangle_number, const float x0, const float y0, const float z0, const float x1,
+                                                         const float y1, const float z1, const float mpc_x, const float mpc_y, const float mpc_z,
+                                                         const int mhd, const uint32_t words) {
+    extern __shared__ __align__(16) unsigned char vox_smem[];
+    TriRecord* rec = reinterpret_cast<TriRecord*>(vox_smem);
+    uint32_t* bitmap = reinterpret_cast<uint32_t*>(rec + VOX_CHUNK);  // [word][thread]
+    const uint32_t col = blockIdx.x * VOX_BLOCK + threadIdx.x;
     const uint32_t A = direction == 0u ? a.ny * a.nz : direction == 1u ? a.nx * a.nz : a.nx * a.ny;
-    if (col >= A) return;
     const int nx = (int)a.nx, ny = (int)a.ny, nz = (int)a.nz;
-    uint32_t cx, cy, cz;  // sim.cl:1163-1168
+    // the column's first cell: where the ray enters the mesh's bounding box (sim.cl:1163-1168)
+    uint32_t cx = 0u, cy = 0u, cz = 0u;
     if (direction == 0u) { cx = (uint32_t)clampi((int)x0 - a.ox, 0, nx - 1); cy = col % a.ny; cz = col / a.ny; }
     else if (direction == 1u) { cx = col / a.nz; cy = (uint32_t)clampi((int)y0 - a.oy, 0, ny - 1); cz = col % a.nz; }
     else { cx = col % a.nx; cy = col / a.nx; cz = (uint32_t)clampi((int)z0 - a.oz, 0, nz - 1); }
-    // position(xyz)+offset, sim.cl:131-133,1169-1170
-    const float3 offset = f3(0.5f * (float)(nx + 2 * a.ox) - 0.5f, 0.5f * (float)(ny + 2 * a.oy) - 0.5f, 0.5f * (float)(nz + 2 * a.oz) - 0.5f);
-    const float3 pos = f3((float)cx + 0.5f - 0.5f * (float)a.nx, (float)cy + 0.5f - 0.5f * (float)a.ny, (float)cz + 0.5f - 0.5f * (float)a.nz);
-    const float3 r_origin = f3(pos.x + offset.x, pos.y + offset.y, pos.z + offset.z);
-    const float3 r_direction = f3((float)(direction == 0u), (float)(direction == 1u), (float)(direction == 2u));
-    uint32_t intersections = 0u, intersections_check = 0u;
-    uint16_t distances[64];
-    const bool outside = direction == 0u ? (r_origin.y < y0 || r_origin.z < z0 || r_origin.y >= y1 || r_origin.z >= z1)
-                         : direction == 1u ? (r_origin.x < x0 || r_origin.z < z0 || r_origin.x >= x1 || r_origin.z >= z1)
-                                           : (r_origin.x < x0 || r_origin.y < y0 || r_origin.x >= x1 || r_origin.y >= y1);
-    if (outside) return;
-    for (uint32_t i = 0u; i < triangle_number; i++) {  // Moeller-Trumbore, sim.cl:1177-1192
-        const uint32_t tx = 3u * i, ty = tx + 1u, tz = ty + 1u;
-        const float3 p0i = f3(p0[tx], p0[ty], p0[tz]);
-        const float3 p1i = f3(p1[tx], p1[ty], p1[tz]);
-        const float3 p2i = f3(p2[tx], p2[ty], p2[tz]);
-        const float3 u = sub3(p1i, p0i), v = sub3(p2i, p0i), w = sub3(r_origin, p0i), h = cross3(r_direction, v), q = cross3(w, u);
-        const float f = 1.0f / dot3(u, h), s = f * dot3(w, h), t = f * dot3(r_direction, q), d = f * dot3(v, q);
-        if (s >= 0.0f && s < 1.0f && t >= 0.0f && s + t < 1.0f) {
-            if (d > 0.0f) {
-                if (intersections < 64u && d < 65536.0f) distances[intersections] = (uint16_t)d;
-                intersections++;
-            } else {
-                intersections_check++;
+    // ray origin in global lattice coordinates: position(xyz) + offset, sim.cl:131-133,1169-1170
+    const float ox = ((float)cx + 0.5f - 0.5f * (float)a.nx) + (0.5f * (float)(nx + 2 * a.ox) - 0.5f);
+    const float oy = ((float)cy + 0.5f - 0.5f * (float)a.ny) + (0.5f * (float)(ny + 2 * a.oy) - 0.5f);
+    const float oz = ((float)cz + 0.5f - 0.5f * (float)a.nz) + (0.5f * (float)(nz + 2 * a.oz) - 0.5f);
+    const float dirx = (float)(direction == 0u), diry = (float)(direction == 1u), dirz = (float)(direction == 2u);
+    bool live = col < A;
+    if (live)  // columns that miss the bounding box do nothing (sim.cl:1174-1176)
+        live = direction == 0u ? !(oy < y0 || oz < z0 || oy >= y1 || oz >= z1)
+               : direction == 1u ? !(ox < x0 || oz < z0 || ox >= x1 || oz >= z1)
+                                 : !(ox < x0 || oy < y0 || ox >= x1 || oy >= y1);
+    for (uint32_t w = 0; w < words; w++) bitmap[w * VOX_BLOCK + threadIdx.x] = 0u;
+    uint32_t ahead = 0u, behind = 0u, dmin = 0xFFFFFFFFu, dmax = 0u;
+    for (uint32_t base = 0u; base < triangle_number; base += VOX_CHUNK) {
+        const uint32_t m = min((uint32_t)VOX_CHUNK, triangle_number - base);
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < m; k += VOX_BLOCK) {  // per-triangle part of the test, once per block
+            const uint32_t i = 3u * (base + k);
+            const float ax = p0[i], ay = p0[i + 1u], az = p0[i + 2u];
+            TriRecord r;
+            r.p0x = ax; r.p0y = ay; r.p0z = az;
+            r.ux = p1[i] - ax; r.uy = p1[i + 1u] - ay; r.uz = p1[i + 2u] - az;
+            r.vx = p2[i] - ax; r.vy = p2[i + 1u] - ay; r.vz = p2[i + 2u] - az;
+            r.hx = diry * r.vz - dirz * r.vy;  // h = dir x v
+            r.hy = dirz * r.vx - dirx * r.vz;
+            r.hz = dirx * r.vy - diry * r.vx;
+            r.f = 1.0f / (r.ux * r.hx + r.uy * r.hy + r.uz * r.hz);
+            r.pad0 = r.pad1 = r.pad2 = 0.0f;
+            rec[k] = r;
+        }
+        __syncthreads();
+        if (!live) continue;
+        for (uint32_t k = 0u; k < m; k++) {
+            const TriRecord& r = rec[k];
+            const float wx = ox - r.p0x, wy = oy - r.p0y, wz = oz - r.p0z;
+            const float sv = r.f * (wx * r.hx + wy * r.hy + wz * r.hz);
+            const float qx = wy * r.uz - wz * r.uy, qy = wz * r.ux - wx * r.uz, qz = wx * r.uy - wy * r.ux;  // q = w x u
+            const float tv = r.f * (dirx * qx + diry * qy + dirz * qz);
+            const float dv = r.f * (r.vx * qx + r.vy * qy + r.vz * qz);
+            if (sv >= 0.0f && sv < 1.0f && tv >= 0.0f && sv + tv < 1.0f) {  // the ray's line crosses the triangle
+                if (dv > 0.0f) {
+                    if (ahead < 64u && dv < 65536.0f) {  // the reference keeps the first 64 hits, as ushort
+                        const uint32_t dist = (uint32_t)dv;
+                        if (dist < 32u * words) bitmap[(dist >> 5) * VOX_BLOCK + threadIdx.x] ^= 1u << (dist & 31u);
+                        dmin = min(dmin, dist);
+                        dmax = max(dmax, dist);
+                    }
+                    ahead++;
+                } else {
+                    behind++;  // second ray, backwards: is the starting point really outside? (error correction)
+                }
             }
         }
     }
-    for (int i = 1; i < (int)intersections && i < 64; i++) {  // insertion sort, sim.cl:1194-1202
-        const uint16_t t = distances[i];
-        int j = i - 1;
-        while (j >= 0 && distances[j] > t) {
-            distances[j + 1] = distances[j];
-            j--;
-        }
-        distances[j + 1] = t;
-    }
-    bool inside = (intersections % 2u) && (intersections_check % 2u);
-    uint32_t intersection = intersections % 2u != intersections_check % 2u;
+    if (!live || ahead == 0u) return;
+    const bool inside0 = (ahead & 1u) && (behind & 1u);
+    const bool skip_nearest = (ahead & 1u) != (behind & 1u);  // start at hit 1 instead of hit 0
     const uint32_t h0 = direction == 0u ? cx : direction == 1u ? cy : cz;
     const uint32_t hmax = direction == 0u ? (uint32_t)clampi((int)x1 - a.ox, 0, nx)
                           : direction == 1u ? (uint32_t)clampi((int)y1 - a.oy, 0, ny)
                                             : (uint32_t)clampi((int)z1 - a.oz, 0, nz);
-    const uint32_t hmesh = intersections ? h0 + (uint32_t)distances[min(intersections - 1u, 63u)] : 0u;
-    for (uint32_t h = h0; h < hmax; h++) {  // sim.cl:1209-1230
-        while (intersection < intersections && h > h0 + (uint32_t)distances[min(intersection, 63u)]) {
-            inside = !inside;
-            intersection++;
+    const uint32_t hend = min(hmax, h0 + dmax);  // nothing is inside at or beyond the farthest stored hit
+    const uint64_t stride = direction == 0u ? 1ull : direction == 1u ? (uint64_t)a.nx : (uint64_t)a.nx * a.ny;
+    uint64_t n = (uint64_t)cx + ((uint64_t)cy + (uint64_t)cz * a.ny) * a.nx;
+    bool below_odd = false;  // parity of the hits strictly below the current cell
+    uint32_t word = 0u;
+    for (uint32_t h = h0; h < hend; h++, n += stride) {
+        const uint32_t m = h - h0;
+        if (m > 0u) {
+            const uint32_t b = m - 1u;
+            if ((b & 31u) == 0u) word = bitmap[(b >> 5) * VOX_BLOCK + threadIdx.x];
+            below_odd ^= (word >> (b & 31u)) & 1u;
         }
-        inside = inside && (intersection < intersections && h < hmesh);
-        const uint64_t n = (direction == 0u ? h : cx) + ((direction == 1u ? h : cy) + (uint64_t)(direction == 2u ? h : cz) * a.ny) * a.nx;
-        if (inside) {
-            const uint8_t flagsn = (uint8_t)((a.flags[n] & (uint8_t)~ION_TYPE_BO) | flag);
-            if (mhd) {  // scratch aliasing of quirk Q15: M / charge parked in B_dyn
+        const bool toggled = skip_nearest ? (m > dmin ? !below_odd : false) : below_odd;
+        if (inside0 != toggled) {
+            a.flags[n] = (uint8_t)((a.flags[n] & (uint8_t)~ION_TYPE_BO) | flag);
+            if (mhd) {  // scratch aliasing of quirk Q15: M / charge parked in B_dyn until initialize
                 if (flag & ION_TYPE_M) {
                     a.B_dyn[n] = mpc_x;
                     a.B_dyn[a.N + n] = mpc_y;
@@ -96,7 +144,6 @@ __global__ void k_voxelize(const __grid_constant__ KArgs a, const uint32_t direc
                     a.B_dyn[n] = mpc_x;
                 }
             }
-            a.flags[n] = flagsn;
         }
     }
 }
@@ -253,8 +300,16 @@ __global__ void __launch_bounds__(SF_BLOCK) k_static_e(const __grid_constant__ K
 cudaError_t launch_voxelize(const KArgs& a, uint32_t direction, uint8_t flag, const float* p0, const float* p1, const float* p2,
                             uint32_t tri, const float* bb6, float mx, float my, float mz, int mhd, cudaStream_t s) {
     const uint32_t A = direction == 0u ? a.ny * a.nz : direction == 1u ? a.nx * a.nz : a.nx * a.ny;
-    k_voxelize<<<(A + 63u) / 64u, 64, 0, s>>>(a, direction, flag, p0, p1, p2, tri, bb6[0], bb6[1], bb6[2], bb6[3], bb6[4], bb6[5], mx,
-                                              my, mz, mhd);
+    // bitmap length: the cells a column can fill, [h0, hmax) -- the bounding box along the ray, clipped to the domain
+    const int n_dir = (int)(direction == 0u ? a.nx : direction == 1u ? a.ny : a.nz), o_dir = direction == 0u ? a.ox : direction == 1u ? a.oy : a.oz;
+    const int lo = clampi((int)bb6[direction] - o_dir, 0, n_dir - 1), hi = clampi((int)bb6[3 + direction] - o_dir, 0, n_dir);
+    const uint32_t words = (uint32_t)((hi > lo ? hi - lo : 0) + 31) / 32u + 1u;
+    const size_t smem = sizeof(TriRecord) * VOX_CHUNK + (size_t)words * VOX_BLOCK * sizeof(uint32_t);
+    if (smem > 200u * 1024u) return cudaErrorInvalidValue;  // a mesh more than ~90 000 cells deep along the ray
+    cudaError_t e = cudaFuncSetAttribute(k_voxelize, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_voxelize<<<(A + VOX_BLOCK - 1u) / VOX_BLOCK, VOX_BLOCK, smem, s>>>(a, direction, flag, p0, p1, p2, tri, bb6[0], bb6[1], bb6[2], bb6[3], bb6[4],
+                                                                          bb6[5], mx, my, mz, mhd, words);
     return cudaGetLastError();
 }
 

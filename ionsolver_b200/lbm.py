@@ -247,6 +247,16 @@ class Lbm:
                                                   magnet_stl.encode() if magnet_stl else None, arr, nd, ctypes.byref(h)))
         return cls(_handle=h)
 
+    @classmethod
+    def setup_scene(cls, name, stl_dir="stl", scale=1.0, subgrid_ecr=False, first_step=False, devices=None):
+        """One of the reference's scene functions by name (setup.rs:22-64): setup_verification, setup_field_vis, setup_ecr_test,
+        setup_mesh_test, setup_mesh_field_test, setup_deeva_test, setup_taylor_green, setup_domain_test."""
+        h = ctypes.c_void_p()
+        arr, nd = _devs(devices)
+        flags = (1 if subgrid_ecr else 0) | (2 if first_step else 0)
+        check(capi.load().ion_setup_scene(name.encode(), str(stl_dir).encode(), float(scale), flags, arr, nd, ctypes.byref(h)))
+        return cls(_handle=h)
+
     def close(self):
         if getattr(self, "handle", None) is not None and self.handle.value:
             for d in self.domains:

@@ -131,7 +131,12 @@ static inline float ddf_load(const Ctx* k, const void* buf, uint64_t o) {
         default: return ((const float*)buf)[o];
     }
 }
+/* Test-infrastructure hook: how many NaNs were handed to the DDF encoders.  A scene that stores NaN has left the domain where
+ * parity is defined: the reference launders NaN through the FP16C bit formula into a finite code that depends on the NaN's sign
+ * and payload, i.e. on the hardware that produced it (x86 default NaN 0xFFC00000 -> -1.5, NVIDIA's 0x7FFFFFFF -> -0). */
+static uint64_t g_nan_stores = 0;
 static inline void ddf_store(const Ctx* k, void* buf, uint64_t o, float x) {
+    if (x != x) __atomic_fetch_add(&g_nan_stores, 1, __ATOMIC_RELAXED);
     switch (k->p->float_type) {
         case 0: ((_Float16*)buf)[o] = (_Float16)(x * 32768.0f); break;  /* vstore_half_rte */
         case 1: ((uint16_t*)buf)[o] = f2h_custom(x); break;
@@ -925,6 +930,11 @@ uint32_t ora_lod_index(const OraParams* p, uint32_t n, uint32_t d) {
     Ctx k;
     make_ctx(&k, p);
     return lod_index(&k, n, d);
+}
+uint64_t ora_nan_stores(int reset) {
+    const uint64_t v = __atomic_load_n(&g_nan_stores, __ATOMIC_RELAXED);
+    if (reset) __atomic_store_n(&g_nan_stores, 0, __ATOMIC_RELAXED);
+    return v;
 }
 int ora_max_threads(void) {
 #ifdef _OPENMP

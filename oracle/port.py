@@ -79,6 +79,8 @@ def lib():
         L.ora_lod_index.argtypes = [P, c.c_uint32, c.c_uint32]
         L.ora_lod_index.restype = c.c_uint32
         L.ora_max_threads.restype = c.c_int
+        L.ora_nan_stores.argtypes = [c.c_int]
+        L.ora_nan_stores.restype = c.c_uint64
         for n in ("ora_stream_collide", "ora_initialize", "ora_update_fields", "ora_clear_qu_lod", "ora_lod_part_2_gather",
                   "ora_update_e_b_dynamic", "ora_transfer", "ora_voxelize_mesh", "ora_psi_from_mesh",
                   "ora_static_b_from_mesh", "ora_static_e_from_mesh", "ora_codec", "ora_neighbors"):
@@ -89,6 +91,12 @@ def lib():
 
 def max_threads() -> int:
     return int(lib().ora_max_threads())
+
+
+def nan_stores(reset=False) -> int:
+    """NaNs handed to the DDF encoders since the last reset (test hook: a scene that stores NaN is outside the domain where
+    parity is defined, see lbm_oracle.c)."""
+    return int(lib().ora_nan_stores(1 if reset else 0))
 
 
 VS_ID = {"D2Q9": 0, "D3Q15": 1, "D3Q19": 2, "D3Q27": 3}

@@ -732,3 +732,7 @@ class RefLbm:
     def precompute_E(self):
         for d in self.domains:
             d.enqueue_precompute_e()
+
+    def precompute_E_ECR(self):  # mod.rs:319-331
+        for d in self.domains:
+            d.enqueue_precompute_e_ecr()

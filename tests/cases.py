@@ -97,8 +97,11 @@ def multi_domain_mhd_cases():
         # cfg4 = D3Q27 x FP16S x MHD x z split x depth 4 (D3Q27 with canonical weights, quirk Q3), cfg5 = D3Q19 x FP16C x MHD x z split x depth 4
         ("mhd_z2_d3q27_fp16s_lod4", _mhd(C(velocity_set="D3Q27", float_type="FP16S", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
                                           ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 16.0)),
+        # (weak coupling: with the strong-coupling units one cell reaches rho_e = 0 at step 5 and stores NaN DDFs, which the
+        # FP16C bit formula launders into a finite code that depends on the NaN's sign and payload, i.e. on the hardware --
+        # tests/test_oracle.py::test_parity_scenes_never_store_nan keeps every scene inside the domain where parity is defined)
         ("mhd_z2_d3q19_fp16c_lod4", _mhd(C(velocity_set="D3Q19", float_type="FP16C", n_x=16, n_y=16, n_z=28, d_z=2, nu=0.05,
-                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True), 16.0)),
+                                          ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4, graphics_active=True), 16.0, weak=True)),
     ]
 
 
@@ -113,8 +116,36 @@ def ragged_mhd_cases():
         ("mhd_z2_d3q19_fp32_lod4_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=32, n_y=16, n_z=64, d_z=2, nu=0.05,
                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
         ("mhd_z3_d3q19_fp16s_lod4_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=16, n_y=32, n_z=48, d_z=3, nu=0.05,
-                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
+                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0, weak=True)),
     ]
+
+
+def drift_scene(float_type="FP32", depth=4, n=(32, 16, 16), velocity_set="D3Q19"):
+    """A WELL-POSED MHD scene for N-step comparisons (returns cfg; fill with `fill_drift_inputs`).
+
+    With every unit set the reference's scenes use, the electron gas is driven bang-bang: its acceleration per step is
+    E * 0.5 / KKGE with KKGE ~ -1e-14 LU (units.rs:175-177), so any field above ~1e-15 LU saturates u_e at the +-c_s clamp with
+    the SIGN of the force (sim_kernels.cl:643-646) and a last-bit difference in E flips cells -- no tolerance survives a few
+    steps, in the reference itself (its LOD sums are float atomics).  Here the velocity unit is 1e8 m/s per lattice unit, which
+    scales KE down to ~8e-17, and there are no static fields: the self-consistent E accelerates the electrons by ~3e-4 c per
+    step -- coupled, smooth, finite for hundreds of steps in FP32, FP16S and FP16C (checked on the oracle)."""
+    c = C(velocity_set=velocity_set, float_type=float_type, n_x=n[0], n_y=n[1], n_z=n[2], nu=0.05, ext_volume_force=True,
+          ext_magneto_hydro=True, mhd_lod_depth=depth, graphics_active=True)
+    c.units.set(float(n[0]), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0e8, 1.2250, 1e-10, 1.0)
+    return c
+
+
+def fill_drift_inputs(lbm, cfg, seed=21):
+    """Smooth seeded rho / u, no solids, no static fields, a net charge of 0.002 per cell modulated along x and y."""
+    fill_inputs(lbm, cfg, seed=seed, smooth=True)
+    for d in lbm.domains:
+        n = d.g.n
+        i = np.arange(n)
+        x, y = i % d.g.n_x, (i // d.g.n_x) % d.g.n_y
+        d.flags[:] = 0
+        d.qc[:] = (RHO_E0 + 0.002 * (1.0 + 0.3 * np.sin(2 * np.pi * x / d.g.n_x) * np.cos(2 * np.pi * y / d.g.n_y))).astype(np.float32)
+        d.e_stat[:] = 0
+        d.b_stat[:] = 0
 
 
 def _ecr(c, length=16.0):

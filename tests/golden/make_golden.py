@@ -129,6 +129,61 @@ def voxel_vectors():
     return out
 
 
+REF_STL = os.path.join(HERE, "stl", "ref")  # the reference's own stl/*.stl, copied as test fixtures
+
+
+def deeva_parts(scale):
+    """Meshes, origins (for a lattice `scale` x 128 cells wide) and model types of setup_deeva_test, setup.rs:423-441."""
+    s = float(scale)
+    return [("deeva_disk_magnet.stl", (64.001 * s, 0.0, 64.0 * s), "Magnet", (0.0, 1000000.0, 0.0)),
+            ("deeva_inlet.stl", (64.0 * s, 0.0, 64.0 * s), "Solid", None),
+            ("deeva_quartz_tube.stl", (64.001 * s, 0.0, 64.0 * s), "Solid", None),
+            ("deeva_ring_magnet.stl", (64.001 * s, -0.5 * s, 64.0 * s), "Magnet", (0.0, 500000.0, 0.0)),
+            ("deeva_e_plate1.stl", (64.0 * s, 0.0, 64.0 * s), "ChargedECR", 0.00000000000021844213 / 2.0),
+            ("deeva_e_plate2.stl", (64.0 * s, 0.0, 64.0 * s), "ChargedECR", -0.00000000000021844213 / 2.0)]
+
+
+def ref_stl_vectors():
+    """The reference's own STL assets through the reference's own voxeliser / static-field kernels:
+    (1) setup_deeva_test (setup.rs:395-446) at its own size 128 x 256 x 128: flags after each of the six meshes;
+    (2) the same scene at half the size (64 x 128 x 64, so that the O(N^2) psi / static_e kernels finish on a CPU):
+        flags, psi, B_stat, E_var;
+    (3) BASELINE cfg2's magnet: disk-magnet.stl repositioned into a 256^3 lattice (pattern of setup.rs:383-384): flags."""
+    out = {}
+    for tag, scale, fields in (("deeva_128x256x128", 1.0, False), ("deeva_64x128x64", 0.5, True)):
+        n = (int(128 * scale), int(256 * scale), int(128 * scale))
+        cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=n[0], n_y=n[1], n_z=n[2], ext_volume_force=True,
+                           ext_magneto_hydro=True, ext_subgrid_ecr=True, mhd_lod_depth=2)
+        cfg.units.set(128.0 * scale, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 10e-8, 1.0, 50000.0)  # setup.rs:397
+        cfg.nu = float(cfg.units.nu_si_lu(0.05))
+        lbm = rh.RefLbm(cfg, threads=0)
+        rec = {"n": list(n), "meshes": []}
+        for i, (f, o, kind, val) in enumerate(deeva_parts(scale)):
+            lbm.import_mesh(open(os.path.join(REF_STL, f), "rb").read(), 1.0, o[0], o[1], o[2], 0.0, 0.0, 0.0)
+            lbm.voxelise_mesh(i, kind, val)
+            fl = lbm.domains[0].flags
+            rec["meshes"].append({"file": f, "origin": list(o), "kind": kind, "value": val, "flags_after": sha(fl),
+                                  "cells_flagged": int((fl != 0).sum())})
+        if fields:
+            lbm.precompute_B()
+            lbm.precompute_E_ECR()
+            d = lbm.domains[0]
+            rec["psi"] = digest(d.e_dyn[: (n[0] + 2) * (n[1] + 2) * (n[2] + 2)])
+            rec["b_stat"] = digest(d.b_stat)
+            rec["e_var"] = digest(d.e_var)
+        out[tag] = rec
+    cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=256, n_y=256, n_z=256, ext_volume_force=True, ext_magneto_hydro=True,
+                       mhd_lod_depth=4)
+    cfg.units.set(256.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
+    lbm = rh.RefLbm(cfg, threads=0)
+    lbm.import_mesh_reposition(open(os.path.join(REF_STL, "disk-magnet.stl"), "rb").read(), 128.1, 128.1, 128.0, 0.0, 0.0, 0.0, 127.0)
+    lbm.voxelise_mesh(0, "Magnet", (0.0, 1000000.0, 0.0))
+    fl = lbm.domains[0].flags
+    out["cfg2_disk_magnet_256"] = {"n": [256, 256, 256], "flags_after": sha(fl), "cells_flagged": int((fl != 0).sum()),
+                                   "p_min": [float(v) for v in lbm.meshes[0].p_min], "p_max": [float(v) for v in lbm.meshes[0].p_max]}
+    return out
+
+
 def main():
     if build_ref.reference_root() is None:
         raise SystemExit("needs /root/reference: golden vectors come from the reference's own kernels")
@@ -141,6 +196,7 @@ def main():
     gold["codecs"] = codec_vectors()
     gold["neighbors"] = neighbor_vectors()
     gold["voxelize"] = voxel_vectors()
+    gold["ref_stl"] = ref_stl_vectors()
     with open(os.path.join(HERE, "reference_vectors.json"), "w") as f:
         json.dump(gold, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "reference_vectors.json"))

@@ -207,6 +207,39 @@ def test_default_and_deterministic_e_b_agree(gpu_lib):
         assert rel_l2(out[False]["b_dyn"], out[True]["b_dyn"]) < TOL_EB_1STEP
 
 
+DRIFT = [("FP32", 4, (32, 16, 16), 100, TOL_RHO_U, TOL_QEB), ("FP32", 3, (32, 32, 16), 100, TOL_RHO_U, TOL_QEB),
+         ("FP16S", 4, (32, 16, 16), 100, TOL_FP16, TOL_FP16), ("FP16C", 4, (32, 16, 16), 100, TOL_FP16, TOL_FP16)]
+
+
+@pytest.mark.parametrize("ft,depth,n,steps,tol_ru,tol_qeb", DRIFT, ids=[f"{d[0]}_lod{d[1]}" for d in DRIFT])
+def test_default_mode_tracks_the_reference_over_100_steps(ft, depth, n, steps, tol_ru, tol_qeb, gpu_lib):
+    """The DEFAULT path -- the one bench.py times: LOD deposit by warp trees and replicas, update_e_b_dynamic as a polyphase
+    FFT convolution -- against the oracle (the C restatement pinned bit-exactly to the reference's kernels), 100 full time steps
+    from the same state on a well-posed scene (cases.drift_scene: the reference's own unit sets drive the electron gas bang-bang
+    on the sign of E, where no tolerance survives a few steps; profiles/r2_drift_curve.md has both curves).
+    Tolerances: FP32 rel-L2 <= 1e-5 for rho, u and <= 1e-4 for Q, E, B; FP16S / FP16C <= 2e-3."""
+    cfg = cases.drift_scene(ft, depth, n)
+    ref = rh.RefLbm(cfg, threads=1, backend="port")
+    cases.fill_drift_inputs(ref, cfg)
+    gpu = product(cfg)
+    cases.upload_inputs(ref, gpu)
+    ref.initialize()
+    gpu.initialize()
+    cases.seed_electron_gas(ref, gpu)
+    assert gpu.domains[0].eb_fft_info()[1] > 0 or True
+    for _ in range(steps):
+        ref.do_time_step()
+        gpu.do_time_step()
+    gpu.finish_queues()
+    rd, gd = ref.domains[0], gpu.domains[0]
+    assert gd.eb_fft_info()[1] > 0, "the polyphase FFT path must be the one under test"
+    assert np.isfinite(rd.e_dyn).all() and np.isfinite(rd.rho).all() and float(np.abs(rd.e_dyn).max()) > 0.0
+    err = {f: rel_l2(gd.read(cases.FIELD_OF[f]), getattr(rd, f)) for f in ("rho", "u", "qc", "e_dyn", "b_dyn")}
+    assert err["rho"] < tol_ru and err["u"] < tol_ru, err
+    assert err["qc"] < tol_qeb and err["e_dyn"] < tol_qeb and err["b_dyn"] < tol_qeb, err
+    gpu.close()
+
+
 MULTI = cases.multi_domain_cases()
 
 
@@ -373,6 +406,52 @@ def test_ion_file_round_trip(gpu_lib, tmp_path):
     assert c.get_d_n() == 6 and c.encode(False) == eb
     for x in (a, b, c):
         x.close()
+
+
+def test_reference_stl_assets_through_the_cuda_voxeliser(golden, gpu_lib):
+    """The reference's own STL files (stl/*.stl, copied to tests/golden/stl/ref as fixtures) through the CUDA voxeliser and
+    static-field kernels, against SHA-256 of what the reference's kernels produce (tests/golden/make_golden.py::ref_stl_vectors):
+    setup_deeva_test's six thruster meshes at the scene's own 128 x 256 x 128 (flags after every mesh), the same scene at
+    64 x 128 x 64 with psi / B_stat / E_var, and cfg2's disk magnet in a 256^3 lattice.  Bit-exact."""
+    from ionsolver_b200 import lbm as L
+    g = golden["ref_stl"]
+    ref_dir = os.path.join(cases.STL_DIR, "ref")
+    kind = {"Solid": L.ModelType.Solid, "Magnet": L.ModelType.Magnet, "Charged": L.ModelType.Charged, "ChargedECR": L.ModelType.ChargedECR}
+    for tag, scale in (("deeva_128x256x128", 1.0), ("deeva_64x128x64", 0.5)):
+        rec = g[tag]
+        n = rec["n"]
+        cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=n[0], n_y=n[1], n_z=n[2], ext_volume_force=True,
+                           ext_magneto_hydro=True, ext_subgrid_ecr=True, mhd_lod_depth=2)
+        cfg.units.set(128.0 * scale, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 10e-8, 1.0, 50000.0)
+        cfg.nu = float(cfg.units.nu_si_lu(0.05))
+        gpu = product(cfg)
+        for i, m in enumerate(rec["meshes"]):
+            o = m["origin"]
+            gpu.import_mesh(os.path.join(ref_dir, m["file"]), 1.0, o[0], o[1], o[2], 0.0, 0.0, 0.0)
+            gpu.voxelise_mesh(i, kind[m["kind"]], m["value"])
+            fl = gpu.domains[0].read(cases.FIELD_OF["flags"])
+            assert int((fl != 0).sum()) == m["cells_flagged"], f"{tag}: cells flagged after {m['file']}"
+            assert sha(fl) == m["flags_after"], f"{tag}: flags after {m['file']}"
+        if "b_stat" in rec:
+            gpu.precompute_B()
+            gpu.precompute_E_ECR()
+            d = gpu.domains[0]
+            assert sha(d.read(cases.FIELD_OF["e_dyn"])[: (n[0] + 2) * (n[1] + 2) * (n[2] + 2)]) == rec["psi"]["sha256"]
+            assert sha(d.read(cases.FIELD_OF["b_stat"])) == rec["b_stat"]["sha256"]
+            assert sha(d.read(cases.FIELD_OF["e_var"])) == rec["e_var"]["sha256"]
+        gpu.close()
+    rec = g["cfg2_disk_magnet_256"]
+    cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=256, n_y=256, n_z=256, ext_volume_force=True, ext_magneto_hydro=True,
+                       mhd_lod_depth=4)
+    cfg.units.set(256.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
+    gpu = product(cfg)
+    gpu.import_mesh_reposition(os.path.join(ref_dir, "disk-magnet.stl"), 128.1, 128.1, 128.0, 0.0, 0.0, 0.0, 127.0)
+    m = gpu.mesh(0)
+    assert [float(v) for v in m["p_min"]] == rec["p_min"] and [float(v) for v in m["p_max"]] == rec["p_max"]
+    gpu.voxelise_mesh(0, L.ModelType.Magnet, (0.0, 1000000.0, 0.0))
+    fl = gpu.domains[0].read(cases.FIELD_OF["flags"])
+    assert int((fl != 0).sum()) == rec["cells_flagged"] and sha(fl) == rec["flags_after"]
+    gpu.close()
 
 
 def test_stl_triangle_count_is_checked_in_64_bits(gpu_lib, tmp_path):

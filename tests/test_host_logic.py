@@ -239,3 +239,63 @@ def test_polyphase_fft_field_update_on_cpu(tmp_path, args):
     res = json.loads(out.stdout.strip().splitlines()[-1])
     assert out.returncode == 0, res
     assert res["rel_l2_E"] < 1e-6 and res["rel_l2_B"] < 1e-6 and res["untouched_bad"] == 0
+
+
+def test_voxeliser_fill_rule_equals_the_reference_state_machine():
+    """The CUDA voxeliser (mesh_kernels.cu) keeps the ray hits of a column as an XOR bitmap and fills by a closed form instead of
+    the reference's sorted list + state machine (sim_kernels.cl:1194-1230).  Both rules, restated in Python, on 100 000 random hit
+    lists -- duplicates, more than 64 hits (only the first 64 are stored), hits beyond the column, every parity of the backward
+    count: identical sets of filled cells."""
+    import random
+
+    def reference_fill(hits, behind, h0, hmax):
+        count = len(hits)
+        if count == 0:
+            return set()
+        dist = sorted(hits[:64])
+        dist += [0] * (64 - len(dist))
+        inside = (count % 2 == 1) and (behind % 2 == 1)
+        k = 1 if (count % 2) != (behind % 2) else 0
+        hmesh = h0 + dist[min(count - 1, 63)]
+        out = set()
+        for h in range(h0, hmax):
+            while k < count and h > h0 + dist[min(k, 63)]:
+                inside = not inside
+                k += 1
+            inside = inside and (k < count and h < hmesh)
+            if inside:
+                out.add(h)
+        return out
+
+    def bitmap_fill(hits, behind, h0, hmax, words):
+        count = len(hits)
+        if count == 0:
+            return set()
+        bits, dmin, dmax = [0] * (32 * words), 1 << 32, 0
+        for i, d in enumerate(hits):
+            if i < 64:
+                if d < 32 * words:
+                    bits[d] ^= 1
+                dmin, dmax = min(dmin, d), max(dmax, d)
+        inside0 = (count % 2 == 1) and (behind % 2 == 1)
+        skip_nearest = (count % 2) != (behind % 2)
+        out, below_odd = set(), False
+        for h in range(h0, min(hmax, h0 + dmax)):
+            m = h - h0
+            if m > 0:
+                below_odd ^= bool(bits[m - 1])
+            toggled = ((not below_odd) if m > dmin else False) if skip_nearest else below_odd
+            if inside0 != toggled:
+                out.add(h)
+        return out
+
+    rng = random.Random(1)
+    for _ in range(100000):
+        ext = rng.choice([5, 17, 40, 100])
+        h0 = rng.randint(0, 3)
+        hmax = h0 + rng.randint(0, ext)
+        n = rng.choice([0, 1, 2, 3, 4, 5, 6, 7, 8, 63, 64, 65, 70, 130]) if rng.random() < 0.3 else rng.randint(0, 9)
+        hits = [rng.randint(0, ext + 5) for _ in range(n)]
+        behind = rng.randint(0, 5)
+        words = (hmax - h0 + 31) // 32 + 1
+        assert reference_fill(hits, behind, h0, hmax) == bitmap_fill(hits, behind, h0, hmax, words), (hits, behind, h0, hmax)

@@ -173,6 +173,26 @@ def test_voxelizer_on_reference_stl_assets():
     assert same_bits(res["ref"][1], res["port"][1])
 
 
+def test_parity_scenes_never_store_nan():
+    """Every MHD parity scene stays finite: no NaN is ever handed to a DDF encoder over the recorded steps (oracle hook
+    ora_nan_stores).  The reference launders NaN through the FP16C bit formula into a finite code that depends on the NaN's sign
+    and payload -- x86's default NaN 0xFFC00000 becomes -1.5, NVIDIA's 0x7FFFFFFF becomes -0 -- so a scene that stores NaN has no
+    hardware-independent reference result."""
+    from oracle import port
+    ragged = {n for n, _ in cases.ragged_mhd_cases()}  # compared after ONE step (tests/test_gpu_parity.py::test_multi_domain_mhd)
+    for name, cfg in cases.all_cases() + cases.ragged_mhd_cases():
+        if not cfg.ext_magneto_hydro or cfg.n_x * cfg.n_y * cfg.n_z > 40000:
+            continue
+        lbm = rh.RefLbm(cfg, threads=1, backend="port")
+        cases.fill_inputs(lbm, cfg)
+        lbm.initialize()
+        cases.seed_electron_gas(lbm)
+        port.nan_stores(reset=True)
+        for _ in range(1 if name in ragged else 8):
+            lbm.do_time_step()
+        assert port.nan_stores(reset=True) == 0, name
+
+
 def test_mass_and_charge_are_conserved_by_the_oracle():
     """Size-independent property the GPU tests reuse at full size: a periodic box without solids conserves sum(rho)."""
     cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=24, n_y=20, n_z=16, nu=0.05, graphics_active=True)

@@ -16,27 +16,32 @@ def diff(tag, ref, gpu, names):
                 idx = np.nonzero(got != want)[0]
                 print(f"  {tag} dom{rd.g.d_i} {n}: {len(idx)} differ, first {idx[:5]} got {got[idx[:3]]} want {want[idx[:3]]}")
 
+ONLY = sys.argv[1] if len(sys.argv) > 1 else ""
+NSTEPS = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 for name, cfg in cases.mhd_cases() + cases.multi_domain_mhd_cases():
+    if ONLY and ONLY not in name:
+        continue
     print("CASE", name, flush=True)
     ref = rh.RefLbm(cfg, threads=1, backend="port"); cases.fill_inputs(ref, cfg)
     gpu = L.Lbm(cases.to_lbm_config(cfg, True), devices=[0]); cases.upload_inputs(ref, gpu)
     ref.initialize(); gpu.initialize()
     names = ["qu_lod", "e_dyn", "b_dyn", "qc", "fi", "ei", "fqi", "u"]
     diff("init", ref, gpu, names)
-    for s in range(2):
+    cases.seed_electron_gas(ref, gpu)
+    for s in range(NSTEPS):
         # piecewise step
         for d in ref.domains: d.enqueue_clear_qu_lod()
         for d in ref.domains: d.enqueue_stream_collide()
         for d in gpu.domains: d.enqueue_clear_qu_lod()
         for d in gpu.domains: d.enqueue_stream_collide(gpu.get_time_step())
-        diff(f"step{s} after stream_collide", ref, gpu, ["qu_lod", "qc", "fi"])
+        diff(f"step{s} after stream_collide", ref, gpu, ["qu_lod", "qc", "fi", "ei", "fqi", "u", "rho"])
         ref.communicate_fi(); gpu.communicate_fi()
         if len(ref.domains) > 1:
             for d in ref.domains: d.enqueue_lod_part_2_gather()
             for d in gpu.domains: d.enqueue_lod_part_2_gather()
         ref.communicate_fqi(); ref.communicate_ei(); ref.communicate_qu_lods()
         gpu.communicate_fqi(); gpu.communicate_ei(); gpu.communicate_qu_lods()
-        diff(f"step{s} after comm", ref, gpu, ["qu_lod"])
+        diff(f"step{s} after comm", ref, gpu, ["qu_lod", "fi", "ei", "fqi"])
         ref.update_e_b_dynamic()
         for d in gpu.domains: d.enqueue_update_e_b_dyn()
         diff(f"step{s} after update_e_b", ref, gpu, ["e_dyn", "b_dyn"])

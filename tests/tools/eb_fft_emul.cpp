@@ -70,7 +70,8 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
         std::fill(accreg.begin(), accreg.end(), 0.0f);
         for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
             const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
-            for (int tid = 0; tid < C::T; tid++) main_phase_product<ND, 1>(tid, kt, shat.data(), nullptr, nullptr, kx0, np, W.data());
+            main_stage_host<ND>(kt, shat.data(), kx0, np, W.data());
+            for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, shat.data(), kx0, np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_z<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_y<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++)
