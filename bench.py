@@ -1,14 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- IonSolver extended-LBM MHD time step on B200: MLUPs/s, roofline and CPU baseline in one JSON line.
+"""bench.py -- IonSolver extended-LBM MHD time step on B200: MLUPs/s, roofline, parity and CPU baseline in one JSON line.
 
-Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`; for N > 1 it is launched under
-torchrun, one rank per GPU.  A "step" is one `Lbm::do_time_step` (clear_qu_lod + stream_collide + update_e_b_dynamic,
-plus halo / LOD exchange when N > 1) over the whole lattice.
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference] [--config cfgX] [--scaling weak|strong]`;
+for N > 1 it is launched under torchrun, one rank per GPU.  A "step" is one `Lbm::do_time_step` (mod.rs:250-272: clear_qu_lod +
+stream_collide + update_e_b_dynamic, plus halo / LOD exchange when N > 1) over the whole lattice.
 
-Workload (BASELINE.json configs[1]): 256^3 D3Q19 FP32 MHD, charged fluid (Q = 0.002/cell, u = (0.1, 0.01, 0), scene of
-setup_bfield_spin, setup.rs:142-201) in the static field of a voxelised disk magnet (synthetic STL with the dimensions
-of stl/disk-magnet.stl; voxelize_mesh + precompute_B, setup.rs:346-393), default mhd_lod_depth = 4.  N GPUs: weak
-scaling, one 256x256x256 z-slab per GPU (d_z = N), halos and LOD pyramids exchanged with NCCL over NVLink.
+Workloads (BASELINE.json `configs`):
+  cfg1  64^3 D3Q19 FP32 Taylor-Green (setup_taylor_green, setup.rs:92-113), no MHD; working set 20 MB, L2 resident
+  cfg2  256^3 D3Q19 FP32 MHD (DEFAULT; the configuration `metric` is quoted on): charged fluid Q = 0.002/cell, u = (0.1, 0.01, 0)
+        (setup_bfield_spin, setup.rs:142-201) in the static field of the reference's stl/disk-magnet.stl, voxelised and turned into
+        B_stat by precompute_B (setup_mesh_field_test, setup.rs:346-393), default mhd_lod_depth = 4
+  cfg3  setup_deeva_test (setup.rs:395-453) with every length doubled: 256 x 512 x 256 (the 512x256x256 of BASELINE.json in the
+        scene's own axis order), six deeva_* STLs, precompute_B + static E of the plates, ext_subgrid_ecr off
+  cfg4  512^3 D3Q27 FP16S MHD, z slabs, strong scaling
+  cfg5  2048 x 2048 x 256 per GPU, D3Q19 FP16C MHD, z slabs, weak scaling (~1.07 G cells / GPU)
+N GPUs: cfg1/2/3/5 weak (one lattice per GPU, d_z = N), cfg4 strong unless --scaling says otherwise; halos and LOD pyramids over
+NCCL / NVLink.
 
 MLUPs/s = lattice cells (halos excluded) x steps / seconds / 1e6 (src/info.rs:73-81).
 """
@@ -28,9 +35,25 @@ for _p in (ROOT, os.path.join(ROOT, "tests")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-N_SIDE = 256
-STL = os.path.join(ROOT, "tests", "golden", "stl", "disk_magnet.stl")
+REF_STL = os.path.join(ROOT, "tests", "golden", "stl", "ref")  # the reference's stl/*.stl, kept as test fixtures
 METRIC = "MLUPs/s"
+
+# per-GPU lattice (weak) or global lattice (strong), kernel family, default scaling
+CONFIGS = {
+    "cfg1": {"n": (64, 64, 64), "vs": "D3Q19", "ft": "FP32", "mhd": False, "scaling": "weak",
+             "what": "64^3 D3Q19 FP32 SRT Taylor-Green (setup_taylor_green), no extensions"},
+    "cfg2": {"n": (256, 256, 256), "vs": "D3Q19", "ft": "FP32", "mhd": True, "scaling": "weak",
+             "what": "256^3 D3Q19 FP32 SRT MHD (volume_force + magneto_hydro), charged fluid Q=0.002 u=(0.1,0.01,0), static B of the "
+                     "voxelised stl/disk-magnet.stl (precompute_B)"},
+    "cfg3": {"n": (256, 512, 256), "vs": "D3Q19", "ft": "FP32", "mhd": True, "scaling": "weak",
+             "what": "setup_deeva_test x2: 256x512x256 D3Q19 FP32 MHD, six deeva_* STLs (ring + disk magnet, quartz tube, inlet, e-plates), "
+                     "precompute_B + static E of the plates, ext_subgrid_ecr off"},
+    "cfg4": {"n": (512, 512, 512), "vs": "D3Q27", "ft": "FP16S", "mhd": True, "scaling": "strong",
+             "what": "512^3 D3Q27 (canonical weights) FP16S MHD, charged fluid, uniform B_stat = (0,0,0.01), z slabs"},
+    "cfg5": {"n": (2048, 2048, 256), "vs": "D3Q19", "ft": "FP16C", "mhd": True, "scaling": "weak",
+             "what": "2048x2048x256 per GPU D3Q19 FP16C MHD, charged fluid, uniform B_stat = (0,0,0.01), z slabs"},
+}
+QSET = {"D2Q9": 9, "D3Q15": 15, "D3Q19": 19, "D3Q27": 27}
 
 
 def measured_peaks():
@@ -41,59 +64,140 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
-# ----------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's own kernels on host cores
-# ----------------------------------------------------------------------------------------------------------------
-SAMPLE_SIDE = 128
+def ncu_traffic():
+    """DRAM bytes per launch of the step's kernels from the committed ncu captures of THIS command (profiles/r2_traffic.json,
+    written by tests/tools/make_profiles.py from `ncu --set full`); None when no capture matches the configuration."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
-def reference_sample_config(lod_depth=4):
-    """Bounded sample of the workload for the CPU arms: same kernels, extensions, LOD depth (so the same 8^depth source
-    terms per cell in update_e_b_dynamic) and units, on a 128^3 lattice instead of 256^3."""
+def bytes_per_cell(cfg):
+    """Algorithmic bytes per cell update: stream_collide and update_e_b_dynamic."""
+    q, s = QSET[cfg["vs"]], (4 if cfg["ft"] == "FP32" else 2)
+    sc = 1 + 4 * q * s + 14 * s + 24 + 4 if cfg["mhd"] else 1 + 2 * q * s
+    return sc, (49 if cfg["mhd"] else 0)
+
+
+def host_threads():
+    """All host cores this process may use -- not OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own kernels on host cores, on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------------------------
+def sample_lattice(cfg):
+    """Bounded sample for the CPU arms: same kernels (velocity set, storage, extensions, LOD depth -> the same 8^depth source
+    terms per cell in update_e_b_dynamic) on a lattice the host finishes in seconds per step."""
+    if not cfg["mhd"]:
+        return (64, 64, 64)
+    return (128, 128, 128) if cfg["vs"] != "D3Q27" else (96, 96, 96)
+
+
+def reference_sample_config(cfg, lod_depth):
     from oracle import ref_host as rh
-    cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=SAMPLE_SIDE, n_y=SAMPLE_SIDE, n_z=SAMPLE_SIDE,
-                       ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=lod_depth, graphics_active=False)
-    cfg.units.set(float(N_SIDE), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
-    cfg.nu = float(cfg.units.nu_si_lu(1.48E-5))
-    return cfg
+    n = sample_lattice(cfg)
+    c = rh.RefConfig(velocity_set=cfg["vs"], float_type=cfg["ft"], n_x=n[0], n_y=n[1], n_z=n[2], ext_volume_force=cfg["mhd"],
+                     ext_magneto_hydro=cfg["mhd"], mhd_lod_depth=lod_depth, graphics_active=False)
+    if cfg["mhd"]:
+        c.units.set(float(cfg["n"][0]), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
+        c.nu = float(c.units.nu_si_lu(1.48E-5))
+    else:
+        c.nu = float(c.units.nu_si_lu(0.1))
+    return c
 
 
-def cpu_reference_run(steps, warmup, lod_depth, threads=0):
-    """Times `steps` Lbm::do_time_step of the reference kernels (oracle/_ref: sim_kernels.cl compiled for the host; the
-    C restatement if that library was not prebuilt) on the sample lattice.  Returns (MLUPs/s, ms/step, kind, cores)."""
-    from oracle import build_ref, port, ref_host as rh
-    cfg = reference_sample_config(lod_depth)
-    geo = rh.domain_geometry(cfg, 0, 0, 0, 0)
-    kind = "reference" if (os.path.isfile(build_ref.lib_path_for(rh.device_defines(cfg, geo))) or build_ref.reference_root()) else "port"
-    cores = threads or port.max_threads()
-    lbm = rh.RefLbm(cfg, threads=cores, backend="ref" if kind == "reference" else "port")
-    d = lbm.domains[0]
-    d.qc[:] = 0.002
-    n = d.g.n
-    d.u[:n] = 0.1
-    d.u[n:2 * n] = 0.01
-    d.b_stat[n:2 * n] = 1e-4  # stands in for the magnet field; static-field values do not change the per-cell work
+def sample_description(cfg, lod_depth):
+    n = sample_lattice(cfg)
+    if not cfg["mhd"]:
+        return f"{n[0]}x{n[1]}x{n[2]} {cfg['vs']} {cfg['ft']} Taylor-Green (the full cfg1 lattice)"
+    return (f"{n[0]}x{n[1]}x{n[2]} {cfg['vs']} {cfg['ft']} MHD sample of the workload: same kernels, extensions, units and LOD depth {lod_depth}, "
+            f"charged fluid Q=0.002 u=(0.1,0.01,0), uniform B_stat=(0,1e-4,0) in place of the voxelised magnet (static-field values do not change "
+            f"the per-cell work)")
+
+
+def fill_sample(lbm_like, is_oracle, cfg):
+    """Identical initial state on the oracle's numpy buffers or on the product's device buffers."""
+    for d in lbm_like.domains:
+        n = d.g.n if is_oracle else d.n
+        if not cfg["mhd"]:  # cfg1: Taylor-Green vortices of setup.rs:458-543 (quirk Q11 included), identical arrays on both sides
+            import cases
+            u, rho = cases.taylor_green_numpy(sample_lattice(cfg)[0])
+            if is_oracle:
+                d.u[:] = u
+                d.rho[:] = rho
+            else:
+                d.write(2, u)
+                d.write(1, rho)
+            continue
+        q = np.full(n, 0.002, np.float32)
+        u = np.zeros(3 * n, np.float32)
+        u[:n] = 0.1
+        u[n:2 * n] = 0.01
+        b = np.zeros(3 * n, np.float32)
+        b[n:2 * n] = 1e-4
+        if is_oracle:
+            d.qc[:] = q
+            d.u[:] = u
+            d.b_stat[:] = b
+        else:
+            d.write(11, q)  # ION_FIELD_Q
+            d.write(2, u)   # ION_FIELD_U
+            d.write(6, b)   # ION_FIELD_B_STAT
+
+
+def cpu_reference_run(cfg, steps, warmup, lod_depth, keep_state=False):
+    """Times `steps` Lbm::do_time_step of the reference kernels (oracle/_ref: sim_kernels.cl compiled for the host; the C
+    restatement if that library was not prebuilt) on the sample lattice.  Returns a dict; with keep_state the oracle object after
+    initialize + ONE step is returned too (bench parity leg)."""
+    from oracle import build_ref, ref_host as rh
+    c = reference_sample_config(cfg, lod_depth)
+    geo = rh.domain_geometry(c, 0, 0, 0, 0)
+    kind = "reference" if (os.path.isfile(build_ref.lib_path_for(rh.device_defines(c, geo))) or build_ref.reference_root()) else "port"
+    cores = host_threads()
+    lbm = rh.RefLbm(c, threads=cores, backend="ref" if kind == "reference" else "port")
+    fill_sample(lbm, True, cfg)
     lbm.initialize()
-    for _ in range(warmup):
+    state = None
+    t_first = time.perf_counter()
+    lbm.do_time_step()
+    t_first = time.perf_counter() - t_first
+    if keep_state:
+        d = lbm.domains[0]
+        # rho / u are only written by the step when graphics are active (UPDATE_FIELDS, domain.rs:856) -- the benchmark runs with
+        # graphics off like a production run, so the DDFs carry the flow state; Q, E, B are written every step
+        state = {k: np.array(getattr(d, k), copy=True) for k in (("fi", "qc", "e_dyn", "b_dyn") if cfg["mhd"] else ("fi",))}
+    for _ in range(max(warmup - 1, 0)):
         lbm.do_time_step()
     t0 = time.perf_counter()
     for _ in range(steps):
         lbm.do_time_step()
-    dt = (time.perf_counter() - t0) / max(steps, 1)
-    return n / dt / 1e6, dt * 1e3, kind, cores
+    dt = (time.perf_counter() - t0) / max(steps, 1) if steps else t_first
+    n = lbm.domains[0].g.n
+    return {"mlups": n / dt / 1e6, "ms": dt * 1e3, "kind": kind, "cores": cores, "state": state, "config": c}
 
 
-def run_reference_arm(args, rank):
-    if rank != 0:
+def run_reference_arm(args, rank, world):
+    if rank != 0:  # under torchrun rank 0 alone runs the CPU arm
         return
-    mlups, ms, kind, cores = cpu_reference_run(args.steps, args.warmup, args.lod_depth)
-    sample = f"{SAMPLE_SIDE}^3 lattice of the same scene (same kernels, LOD depth {args.lod_depth}), {args.steps} full time steps"
+    cfg = CONFIGS[args.config]
+    r = cpu_reference_run(cfg, args.steps, args.warmup, args.lod_depth)
+    sample = f"{sample_description(cfg, args.lod_depth)}; {args.steps} full time steps after {args.warmup} warm-up"
+    conf = workload_config(args, world)
+    conf["reference_arm_runs"] = sample  # the CPU arm times a bounded sample of the workload, not the full lattice
+    conf["same_lattice_as_gpu_arm"] = False
     line = {
-        "impl": "reference", "metric": METRIC, "value": mlups, "unit": "MLUPs/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload_config(args),
-        "cpu_baseline": {"value": mlups, "unit": "MLUPs/s", "cores": cores, "kind": kind, "sample": sample},
-        "e2e": {"value": mlups, "unit": "MLUPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": r["mlups"], "unit": "MLUPs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms"], "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": conf,
+        "cpu_baseline": {"value": r["mlups"], "unit": "MLUPs/s", "cores": r["cores"], "kind": r["kind"], "sample": sample},
+        "e2e": {"value": r["mlups"], "unit": "MLUPs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -102,11 +206,28 @@ def run_reference_arm(args, rank):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
-def workload_config(args):
-    return {"workload": f"cfg2: {N_SIDE}^3 D3Q19 FP32 SRT MHD (volume_force + magneto_hydro), charged fluid Q=0.002 u=(0.1,0.01,0), "
-                        f"static B of a voxelised disk magnet, mhd_lod_depth={args.lod_depth}",
-            "lattice_per_gpu": [N_SIDE, N_SIDE, N_SIDE], "decomposition": f"d_z={args.gpus} z-slabs, one per GPU",
-            "cache": "working set 7.3 GB per GPU >> 126 MB L2: every step streams from HBM, no L2 flush needed"}
+def scaling_of(args):
+    return args.scaling or CONFIGS[args.config]["scaling"]
+
+
+def lattice_of(args, world):
+    """(global lattice, per-GPU lattice) for the run."""
+    n = CONFIGS[args.config]["n"]
+    if args.cells_z:
+        n = (n[0], n[1], args.cells_z)
+    if scaling_of(args) == "weak":
+        return (n[0], n[1], n[2] * world), n
+    return n, (n[0], n[1], n[2] // world)
+
+
+def workload_config(args, world):
+    cfg = CONFIGS[args.config]
+    g, l = lattice_of(args, world)
+    ws = float(np.prod(l)) * (sum(bytes_per_cell(cfg)) + (60 if cfg["mhd"] else 16)) / 1e9
+    return {"workload": f"{args.config}: {cfg['what']}" + (f", mhd_lod_depth={args.lod_depth}" if cfg["mhd"] else ""),
+            "lattice_global": list(g), "lattice_per_gpu": list(l), "decomposition": f"d_z={world} z-slabs, one per GPU",
+            "cache": (f"working set ~{ws:.1f} GB per GPU >> 126 MB L2: every step streams from HBM, no L2 flush needed" if ws > 1.0 else
+                      f"working set ~{ws * 1e3:.0f} MB per GPU: L2 resident (reported, not used for the HBM claim)")}
 
 
 class ClockSampler:
@@ -137,8 +258,8 @@ class ClockSampler:
             self.stop.wait(0.1)
 
     def _run_nvml(self):
-        """Same quantities through NVML (nvidia_ml_py): a query takes microseconds, so a 0.5 s timed region gets ~50 samples instead
-        of the one or two an nvidia-smi process manages.  Returns False (-> nvidia-smi loop) when NVML is not usable."""
+        """Same quantities through NVML (nvidia_ml_py): a query takes microseconds, so a short timed region still gets tens of
+        samples.  Returns False (-> nvidia-smi loop) when NVML is not usable."""
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -161,7 +282,7 @@ class ClockSampler:
                         self.reasons.add(n)
             except Exception:
                 pass
-            self.stop.wait(0.01)
+            self.stop.wait(0.005)
         return True
 
     def __enter__(self):
@@ -178,26 +299,72 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
-def build_scene(args, rank, world, device):
-    """cfg2 through the public host API (LbmConfig/Lbm of mod.rs): returns an initialised Lbm."""
-    from ionsolver_b200 import lbm as L
-    cfg = L.LbmConfig(velocity_set=L.VelocitySet.D3Q19, relaxation_time=L.RelaxationTime.Srt, float_type=L.FloatType.FP32,
-                      n_x=N_SIDE, n_y=N_SIDE, n_z=N_SIDE * world, d_z=world, ext_volume_force=True, ext_magneto_hydro=True,
-                      mhd_lod_depth=args.lod_depth, graphics_config=L.GraphicsConfig(False))
-    cfg.units.set(float(N_SIDE), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
-    cfg.nu = cfg.units.nu_si_lu(1.48E-5)
+def make_lbm(L, cfg_l, rank, world, device):
     if world == 1:
-        lbm = L.Lbm(cfg, devices=[device])
+        return L.Lbm(cfg_l, devices=[device])
+    import torch
+    import torch.distributed as dist
+    ident = [L.Lbm.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    lbm = L.Lbm.new_distributed(cfg_l, rank, world, device, ident[0])
+    torch.cuda.synchronize()
+    return lbm
+
+
+def build_scene(args, rank, world, device):
+    """The workload through the public host API (LbmConfig / Lbm of mod.rs, scene code of setup.rs): an initialised Lbm."""
+    from ionsolver_b200 import lbm as L
+    cfg = CONFIGS[args.config]
+    g, _ = lattice_of(args, world)
+    vs = {"D3Q19": L.VelocitySet.D3Q19, "D3Q27": L.VelocitySet.D3Q27}[cfg["vs"]]
+    ft = {"FP32": L.FloatType.FP32, "FP16S": L.FloatType.FP16S, "FP16C": L.FloatType.FP16C}[cfg["ft"]]
+    c = L.LbmConfig(velocity_set=vs, relaxation_time=L.RelaxationTime.Srt, float_type=ft, n_x=g[0], n_y=g[1], n_z=g[2], d_z=world,
+                    ext_volume_force=cfg["mhd"], ext_magneto_hydro=cfg["mhd"], mhd_lod_depth=args.lod_depth,
+                    graphics_config=L.GraphicsConfig(False))
+    if args.config == "cfg1":
+        c.nu = c.units.nu_si_lu(0.1)
+        lbm = make_lbm(L, c, rank, world, device)
+        lbm.set_taylor_green(1)
+        lbm.initialize()
+        return lbm
+    if args.config == "cfg3":
+        c.units.set(256.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 10e-8, 1.0, 50000.0)  # setup.rs:397 with lbm_length x2
+        c.nu = c.units.nu_si_lu(0.05)
+        c.ecr_freq = c.units.time_lu_si(2.45E9)
+        lbm = make_lbm(L, c, rank, world, device)
+        s = 2.0
+        zc = 64.0 * s * world if scaling_of(args) == "weak" else 64.0 * s  # the thruster sits in the middle of the global lattice
+        parts = [("deeva_disk_magnet.stl", 64.001 * s, 0.0, L.ModelType.Magnet, (0.0, 1000000.0, 0.0)),
+                 ("deeva_inlet.stl", 64.0 * s, 0.0, L.ModelType.Solid, None),
+                 ("deeva_quartz_tube.stl", 64.001 * s, 0.0, L.ModelType.Solid, None),
+                 ("deeva_ring_magnet.stl", 64.001 * s, -0.5 * s, L.ModelType.Magnet, (0.0, 500000.0, 0.0)),
+                 ("deeva_e_plate1.stl", 64.0 * s, 0.0, L.ModelType.ChargedECR, 0.00000000000021844213 / 2.0),
+                 ("deeva_e_plate2.stl", 64.0 * s, 0.0, L.ModelType.ChargedECR, -0.00000000000021844213 / 2.0)]
+        for i, (f, ox, oy, kind, val) in enumerate(parts):
+            lbm.import_mesh(os.path.join(REF_STL, f), 1.0, ox, oy, zc, 0.0, 0.0, 0.0)
+            lbm.voxelise_mesh(i, kind, val)
+        lbm.precompute_B()
+        lbm.precompute_E()
+        for d in lbm.domains:
+            d.write(11, np.full(d.n, 0.002, np.float32))
+        lbm.setup_velocity_field((0.0, 0.05, 0.0), 1.0)  # propellant flowing along the tube axis
+        lbm.initialize()
+        return lbm
+    # cfg2 / cfg4 / cfg5: charged fluid of setup_bfield_spin (setup.rs:144,182-197)
+    c.units.set(float(cfg["n"][0]), 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 0.0000000001, 1.0)
+    c.nu = c.units.nu_si_lu(1.48E-5)
+    lbm = make_lbm(L, c, rank, world, device)
+    if args.config == "cfg2":
+        n = cfg["n"][0]
+        lbm.import_mesh_reposition(os.path.join(REF_STL, "disk-magnet.stl"), 0.5 * n + 0.1, 0.5 * n + 0.1, 0.5 * g[2], 0.0, 0.0, 0.0, 0.5 * n - 1.0)
+        lbm.voxelise_mesh(0, L.ModelType.Magnet, (0.0, 1000000.0, 0.0))
+        lbm.precompute_B()
     else:
-        import torch
-        import torch.distributed as dist
-        ident = [L.Lbm.comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ident, src=0)
-        lbm = L.Lbm.new_distributed(cfg, rank, world, device, ident[0])
-        torch.cuda.synchronize()
-    lbm.import_mesh_reposition(STL, 0.5 * N_SIDE + 0.1, 0.5 * N_SIDE + 0.1, 0.5 * N_SIDE * world, 0.0, 0.0, 0.0, 0.5 * N_SIDE - 1.0)
-    lbm.voxelise_mesh(0, L.ModelType.Magnet, (0.0, 1000000.0, 0.0))
-    lbm.precompute_B()
+        for d in lbm.domains:  # uniform B_stat = (0, 0, 0.01) LU written like a scene would (setup.rs:182-190)
+            b = np.zeros(3 * d.n, np.float32)
+            b[2 * d.n:] = 0.01
+            d.write(6, b)
+            del b
     for d in lbm.domains:
         d.write(11, np.full(d.n, 0.002, np.float32))  # ION_FIELD_Q
     lbm.setup_velocity_field((0.1, 0.01, 0.0), 1.0)
@@ -205,11 +372,41 @@ def build_scene(args, rank, world, device):
     return lbm
 
 
+def gpu_sample_parity(args, device, cpu_state, ref_cfg):
+    """Parity of the timed path against the reference at the CPU arm's sample size: the SAME sample scene is built on the GPU,
+    both sides run initialize + one time step from identical state, and the fields are compared (relative L2)."""
+    from ionsolver_b200 import lbm as L
+    import cases
+    from oracle_util import rel_l2
+    cfg = CONFIGS[args.config]
+    g = L.Lbm(cases.to_lbm_config(ref_cfg), devices=[device])
+    fill_sample(g, False, cfg)
+    g.initialize()
+    g.do_time_step()
+    g.finish_queues()
+    d = g.domains[0]
+    ids = {"fi": 0, "rho": 1, "u": 2, "qc": 11, "e_dyn": 7, "b_dyn": 8}
+    out = {}
+    for k, want in cpu_state.items():
+        got = np.asarray(d.read(ids[k]))
+        got = got.view(want.dtype) if got.dtype != want.dtype else got
+        out[k] = {"bit_exact": bool(got.tobytes() == want.tobytes())}
+        if want.dtype == np.float32:
+            out[k]["rel_l2"] = float(rel_l2(got, want))
+        else:
+            out[k]["stored_words_differing"] = int((got != want).sum())
+    fft = d.eb_fft_info() if cfg["mhd"] else (0, 0)
+    g.close()
+    return {"what": "GPU default path vs the reference kernels on the CPU: same sample scene, initialize + 1 step from identical state",
+            "lattice": [ref_cfg.n_x, ref_cfg.n_y, ref_cfg.n_z], "fields": out, "polyphase_fft_tasks": int(fft[1])}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     from ionsolver_b200 import capi
     if not torch.cuda.is_available() or capi.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; ionsolver_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    cfg = CONFIGS[args.config]
     dist = None
     # NCCL prints its version banner to stdout; the driver wants exactly one JSON line there, so everything up to the final
     # print goes to stderr
@@ -222,11 +419,16 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
     torch.cuda.set_device(device)
+    t_build = time.perf_counter()
     lbm = build_scene(args, rank, world, device)
+    lbm.finish_queues()
+    t_build = time.perf_counter() - t_build
     dom = lbm.domains[0]
     stream = torch.cuda.ExternalStream(dom.stream(), device=device)
-    cells_local = N_SIDE ** 3
-    cells_global = cells_local * world
+    g_lat, l_lat = lattice_of(args, world)
+    cells_local = int(np.prod(l_lat))
+    cells_global = int(np.prod(g_lat))
+    mhd = cfg["mhd"]
 
     def barrier():
         lbm.finish_queues()
@@ -261,96 +463,94 @@ def run_ours(args, rank, world, local_rank):
     value = cells_global / (ms_step * 1e-3) / 1e6
 
     # ---- per-kernel durations inside the step (CUDA events on the launching stream) ----
-    kern_ms = {"clear_qu_lod": 0.0, "stream_collide": 0.0, "update_e_b_dynamic": 0.0}
+    names = ["clear_qu_lod", "stream_collide", "update_e_b_dynamic"] if mhd else ["stream_collide"]
+    kern_ms = {k: 0.0 for k in names}
     k_prof = min(args.steps, 10)
-    if True:  # every rank times its own kernels (no collective inside these three calls); rank 0 reports
-        evs = []
-        barrier()
-        t = lbm.get_time_step()
-        for s in range(k_prof):
-            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-            e[0].record(stream)
+    evs = []
+    barrier()
+    t = lbm.get_time_step()
+    for s in range(k_prof):  # every rank times its own kernels (no collective inside these calls)
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e[0].record(stream)
+        if mhd:
             dom.enqueue_clear_qu_lod()
-            e[1].record(stream)
-            dom.enqueue_stream_collide(t + s)
-            e[2].record(stream)
+        e[1].record(stream)
+        dom.enqueue_stream_collide(t + s)
+        e[2].record(stream)
+        if mhd:
             dom.enqueue_update_e_b_dyn()
-            e[3].record(stream)
-            evs.append(e)
-        lbm.set_time_step(t + k_prof)
-        barrier()
-        for e in evs:
+        e[3].record(stream)
+        evs.append(e)
+    lbm.set_time_step(t + k_prof)
+    barrier()
+    for e in evs:
+        if mhd:
             kern_ms["clear_qu_lod"] += e[0].elapsed_time(e[1]) / k_prof
-            kern_ms["stream_collide"] += e[1].elapsed_time(e[2]) / k_prof
             kern_ms["update_e_b_dynamic"] += e[2].elapsed_time(e[3]) / k_prof
+        kern_ms["stream_collide"] += e[1].elapsed_time(e[2]) / k_prof
     if dist is not None:  # slabs differ in how many foreign LOD sources they sum over: report the slowest rank's kernels
         tk = torch.tensor([kern_ms[k] for k in sorted(kern_ms)], device=f"cuda:{device}", dtype=torch.float64)
         dist.all_reduce(tk, op=dist.ReduceOp.MAX)
         kern_ms = {k: float(v) for k, v in zip(sorted(kern_ms), tk.tolist())}
     peaks, peak_kind = measured_peaks()
     hbm_peak = float(peaks["hbm_gbs"])
-    sc_bytes = 1 + 4 * 19 * 4 + 14 * 4 + 24 + 4   # 389 B/cell: MHD stream_collide, D3Q19 FP32
-    eb_bytes = 49                                 # update_e_b_dynamic
-    pairs = cells_local * (8 ** args.lod_depth)   # (cell, LOD source) terms of the own pyramid; 9 FMA = 18 flop each
-    kernels = {}
-    roofline = None
-    if True:
-        fma_peak = capi.measure_fma_peak(device, packed=False)   # FMA/s, scalar FFMA, measured now on this GPU
-        fma_peak_packed = capi.measure_fma_peak(device, packed=True)
-        sc_gbs = cells_local * sc_bytes / (kern_ms["stream_collide"] * 1e-3) / 1e9
-        eb_gbs = cells_local * eb_bytes / (kern_ms["update_e_b_dynamic"] * 1e-3) / 1e9
-        eb_tflops = pairs * 18 / (kern_ms["update_e_b_dynamic"] * 1e-3) / 1e12
-        kernels = {
-            "stream_collide": {"ms": kern_ms["stream_collide"], "bound": "hbm", "bytes_per_cell": sc_bytes, "achieved_gbs": sc_gbs,
-                               "frac_of_hbm_peak": sc_gbs / hbm_peak, "share_of_step": kern_ms["stream_collide"] / ms_step},
-            "update_e_b_dynamic": {"ms": kern_ms["update_e_b_dynamic"], "bound": "fp32 FMA issue (8^depth source terms per cell, 9 FMA each)",
-                                   "bytes_per_cell": eb_bytes, "achieved_gbs": eb_gbs, "frac_of_hbm_peak": eb_gbs / hbm_peak,
-                                   "pairs_per_s": pairs / (kern_ms["update_e_b_dynamic"] * 1e-3), "achieved_tflops": eb_tflops,
-                                   "fp32_peak_tflops": 2 * fma_peak / 1e12, "fp32_peak_tflops_packed": 2 * fma_peak_packed / 1e12,
-                                   "frac_of_fp32_peak": eb_tflops / (2 * fma_peak / 1e12),
-                                   "share_of_step": kern_ms["update_e_b_dynamic"] / ms_step,
-                                   "pairs_note": "pairs = cells x 8^depth, the reference's loop count (sim.cl:943); LOD rows whose entries "
-                                                 "are all zero are skipped by the kernel (in a single-domain run 585 of the 4096 window slots "
-                                                 "are never filled, quirk Q5), so the executed FMA rate is ~14 % below achieved_tflops there"},
-            "clear_qu_lod": {"ms": kern_ms["clear_qu_lod"], "share_of_step": kern_ms["clear_qu_lod"] / ms_step},
-        }
-        # The roofline object is for the dominant kernel of the step.  When that is update_e_b_dynamic (LOD depth 4) the HBM
-        # fraction is tiny by construction -- the kernel is bound by CUDA-core FP32 issue, neither by HBM nor by tensor cores
-        #  -- so its FP32 roofline is attached under "compute", and stream_collide's HBM roofline under "hbm_kernel".
-        dom_name = max(("stream_collide", "update_e_b_dynamic"), key=lambda k: kernels[k]["ms"])
-        hbm_kernel = {"kernel": "stream_collide", "bound": "hbm", "achieved": sc_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": sc_gbs / hbm_peak,
-                      "algorithmic_bytes_per_launch": cells_local * sc_bytes, "ms_per_launch": kern_ms["stream_collide"],
-                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind})", "traffic": 6.477e9,
-                      "traffic_source": "profiles/r1_ncu_stream_collide.md (ncu --set full): dram__bytes_read.sum 3.442 GB + dram__bytes_write.sum 3.035 GB per launch"}
-        if dom_name == "update_e_b_dynamic":
-            # The dominant kernel of the step at this LOD depth is bound by CUDA-core FP32 issue -- neither by HBM (49 B per cell
-            # against 8^depth x 18 flop) nor by tensor cores -- so its roofline is stated in FP32 TFLOP/s against
-            # the FFMA issue peak measured in this process; the HBM-bound kernel of the step follows under "hbm_kernel".
-            roofline = {"kernel": dom_name, "bound": "fp32", "achieved": eb_tflops, "peak": 2 * fma_peak / 1e12, "unit": "TFLOP/s",
-                        "frac": eb_tflops / (2 * fma_peak / 1e12), "flop_per_launch": pairs * 18, "ms_per_launch": kern_ms["update_e_b_dynamic"],
-                        "peak_source": "scalar FFMA issue micro-benchmark run in this process on this GPU (ion_measure_fma_peak); "
-                                       "MEASURED_PEAKS.json has no FP32 entry",
-                        "traffic": 0.792e9, "traffic_source": "profiles/r1_ncu_update_e_b_pair.md: dram__bytes_read.sum + dram__bytes_write.sum",
-                        "hbm_view": {"algorithmic_bytes_per_launch": cells_local * eb_bytes, "achieved_gbs": eb_gbs, "frac_of_hbm_peak": eb_gbs / hbm_peak},
-                        "hbm_kernel": hbm_kernel,
-                        "note": "bound is 'fp32' (CUDA cores), outside the hbm|tensor pair: see DESIGN.md 4.2 for why; 'hbm_kernel' is stream_collide"}
-        else:
-            roofline = dict(hbm_kernel)
+    sc_bytes, eb_bytes = bytes_per_cell(cfg)
+    cells_halo = dom.n  # the kernels also stream the two halo layers of a slab; algorithmic bytes are counted on lattice cells only
+    traffic = ncu_traffic().get(args.config, {}) if world == 1 else {}
+    fft_bytes, fft_tasks = dom.eb_fft_info() if mhd else (0, 0)
+
+    def hbm_view(name, bpc, extra=None):
+        ms = kern_ms[name]
+        gbs = cells_local * bpc / (ms * 1e-3) / 1e9
+        o = {"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+             "algorithmic_bytes_per_cell": bpc, "algorithmic_bytes_per_launch": cells_local * bpc, "ms_per_launch": ms,
+             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_kind}; burst copy figure)",
+             "traffic": traffic.get(name, {}).get("dram_bytes"), "traffic_source": traffic.get(name, {}).get("source")}
+        if extra:
+            o.update(extra)
+        return o
+
+    kernels = {"stream_collide": hbm_view("stream_collide", sc_bytes)}
+    kernels["stream_collide"]["share_of_step"] = kern_ms["stream_collide"] / ms_step
+    if mhd:
+        eb = hbm_view("update_e_b_dynamic", eb_bytes, {
+            "algorithm": ("polyphase FFT convolution (eb_fft.cu): k_eb_src + k_eb_fft, one block per in-block offset"
+                          if fft_tasks else "direct summation over the LOD sources (fields.cu)"),
+            "polyphase_fft_tasks": int(fft_tasks), "static_kernel_spectra_bytes": int(fft_bytes),
+            "streamed_bytes_per_launch": cells_local * eb_bytes + int(fft_bytes),
+            "streamed_frac_of_hbm_peak": (cells_local * eb_bytes + int(fft_bytes)) / (kern_ms["update_e_b_dynamic"] * 1e-3) / 1e9 / hbm_peak,
+            "equivalent_direct_pair_terms_per_s": cells_local * (8 ** args.lod_depth) / (kern_ms["update_e_b_dynamic"] * 1e-3),
+            "note": "`achieved` counts SURVEY 8d's 49 B per cell only; the kernel also streams its static kernel spectra (102 B per cell) once "
+                    "per step -- `streamed_*` includes them.  The reference algorithm sums 8^depth source terms per cell here."})
+        eb["share_of_step"] = kern_ms["update_e_b_dynamic"] / ms_step
+        kernels["update_e_b_dynamic"] = eb
+        kernels["clear_qu_lod"] = {"ms": kern_ms["clear_qu_lod"], "share_of_step": kern_ms["clear_qu_lod"] / ms_step}
+    dom_name = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_launch"])
+    roofline = {k: v for k, v in kernels[dom_name].items() if k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source",
+                                                                     "algorithmic_bytes_per_launch", "ms_per_launch", "peak_source")}
+    step_bytes = cells_local * (sc_bytes + eb_bytes)
+    roofline["whole_step"] = {"algorithmic_bytes_per_cell": sc_bytes + eb_bytes, "achieved_gbs": step_bytes / (ms_step * 1e-3) / 1e9,
+                              "frac_of_hbm_peak": step_bytes / (ms_step * 1e-3) / 1e9 / hbm_peak,
+                              "note": "north_star's figure: fused MHD stream_collide + field update against the HBM roofline"}
+    roofline["other_kernels"] = {k: {kk: v[kk] for kk in ("achieved", "frac", "ms_per_launch", "traffic")} for k, v in kernels.items()
+                                 if k != dom_name and "achieved" in v}
 
     # ---- end to end through the public API with HOST buffers: load state -> initialize -> step -> save state ----
     e2e = None
-    if True:  # at N GPUs every rank uploads / downloads the sections of its own slab; initialize and the step exchange halos
+    host_bytes = dom.n * 21 if mhd else dom.n * 17
+    if host_bytes < 12e9:  # at N GPUs every rank uploads / downloads the sections of its own slab
         n = dom.n
-        host = {name: torch.empty(sz, dtype=dt, pin_memory=True) for name, sz, dt in
-                (("flags", n, torch.uint8), ("rho", n, torch.float32), ("u", 3 * n, torch.float32), ("q", n, torch.float32))}
-        ids = {"flags": 3, "rho": 1, "u": 2, "q": 11}
-        for name, tns in host.items():
-            tns.numpy()[:] = dom.read(ids[name])
+        sections = [("flags", n, torch.uint8, 3), ("rho", n, torch.float32, 1), ("u", 3 * n, torch.float32, 2)]
+        if mhd:
+            sections.append(("q", n, torch.float32, 11))
+        host = {name: (torch.empty(sz, dtype=dt, pin_memory=True), fid) for name, sz, dt, fid in sections}
+        for name, (tns, fid) in host.items():
+            tns.numpy()[:] = dom.read(fid)
         lib = capi.load()
 
         def io(fn):
-            for name, tns in host.items():
-                capi.check(fn(dom.handle, ids[name], ctypes.c_void_p(tns.data_ptr()), 0, tns.numel() * tns.element_size()))
+            for name, (tns, fid) in host.items():
+                capi.check(fn(dom.handle, fid, ctypes.c_void_p(tns.data_ptr()), 0, tns.numel() * tns.element_size()))
 
         def e2e_step():
             io(lib.ion_buffer_write)          # the .ion sections a loader uploads (file.rs:118-152), from pinned memory
@@ -361,8 +561,8 @@ def run_ours(args, rank, world, local_rank):
 
         e2e_step()
         k_e2e = max(3, min(args.steps, 5))
-        t0 = time.perf_counter()
         barrier()
+        t0 = time.perf_counter()
         for _ in range(k_e2e):
             e2e_step()
         barrier()
@@ -371,34 +571,22 @@ def run_ours(args, rank, world, local_rank):
             tt = torch.tensor([dt], device=f"cuda:{device}", dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dt = float(tt.item())
-        nbytes = sum(t.numel() * t.element_size() for t in host.values()) * world
+        nbytes = sum(t.numel() * t.element_size() for t, _ in host.values()) * world
         e2e = {"value": cells_global / dt / 1e6, "unit": "MLUPs/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "what": "per step: upload flags/rho/u/Q from pinned host memory, Lbm::initialize, "
+               "ms_per_step": dt * 1e3, "host_link_gbs_aggregate": 2 * nbytes / dt / 1e9,
+               "what": "per step: upload flags/rho/u/Q from pinned host memory, Lbm::initialize, "
                "Lbm::do_time_step, download flags/rho/u/Q (the load -> step -> save cycle of file.rs through the C ABI)"}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        mlups, ms, kind, cores = cpu_reference_run(2, 1, args.lod_depth)
-        cpu = {"value": mlups, "unit": "MLUPs/s", "cores": cores, "kind": kind, "ms_per_step": ms,
-               "sample": f"{SAMPLE_SIDE}^3 lattice of the same scene (same kernels, LOD depth {args.lod_depth}), 2 timed full time steps after 1 warm-up"}
-
-    # Source terms per cell that update_e_b_dynamic sums (sim.cl:940-983).  They GROW with the number of domains -- the own window
-    # is fully populated only in multi-domain runs (quirk Q5 leaves 585 of its 4096 slots empty in a single domain, and all-zero
-    # rows are skipped) and every other slab adds its pyramid level max(depth - distance, 0) -- so MLUPs/s per GPU falls with N at
-    # constant work per SOURCE TERM; this is the reference's algorithm, not communication (halos and LODs overlap with the update).
-    D = args.lod_depth
-    own_fine = 8 ** D
-    if world == 1:
-        empty = sum(8 ** i for i in range(D))
-        terms = {"own": own_fine - (empty // (2 ** D)) * (2 ** D), "foreign_max": 0}
+        del host
     else:
-        # only slabs with a LOWER index count: for the others the reference's `domain_diff * DEF_N` is a negative int times a uint,
-        # which wraps to ~4.29e9 cells (quirk Q18) -- their terms are < 1e-16 of the sums and the fast path skips them
-        terms = {"own": own_fine, "foreign_max": max(sum(8 ** max(D - (r - o), 0) for o in range(r)) for r in range(world))}
-    terms["per_cell_slowest_rank"] = terms["own"] + terms["foreign_max"]
-    terms["note"] = ("update_e_b_dynamic work per cell depends on the domain count (reference algorithm: LOD window quirk Q5 + foreign pyramids); "
-                     "compare runs by source terms per second, not only by MLUPs/s")
-    terms["source_terms_per_s_per_gpu"] = terms["per_cell_slowest_rank"] * cells_local / (kern_ms["update_e_b_dynamic"] * 1e-3)
+        e2e = {"value": None, "unit": "MLUPs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+               "what": f"skipped: {host_bytes / 1e9:.0f} GB of pinned host staging per rank"}
+
+    cpu, parity = None, None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(cfg, 2, 1, args.lod_depth, keep_state=True)
+        cpu = {"value": r["mlups"], "unit": "MLUPs/s", "cores": r["cores"], "kind": r["kind"], "ms_per_step": r["ms"],
+               "sample": f"{sample_description(cfg, args.lod_depth)}; 2 timed full time steps after 1 warm-up"}
+        parity = gpu_sample_parity(args, device, r["state"], r["config"])
 
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -406,9 +594,9 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "MLUPs/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "kernels": kernels, "lod_source_terms": terms, "cpu_baseline": cpu,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling_of(args), "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "kernels": kernels, "cpu_baseline": cpu, "parity": parity, "scene_build_s": t_build,
         }
         print(json.dumps(line), flush=True)
     lbm.close()
@@ -423,14 +611,17 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"], help="default: the configuration's own (cfg4 strong, others weak)")
     ap.add_argument("--lod-depth", type=int, default=4, help="mhd_lod_depth (reference default 4, mod.rs:126)")
+    ap.add_argument("--cells-z", type=int, default=0, help="override the z extent of the configuration's lattice (memory-limited boxes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        run_reference_arm(args, rank)
+        run_reference_arm(args, rank, world)
         return
     if world != args.gpus:
         if args.gpus > 1:

@@ -21,6 +21,7 @@ struct EbFftPlan {
     Task* tasks;
     float2* khat;
     float2* shat;
+    float* scratch;  // the sums of a step before they are combined with the static fields: 6 floats per cell, rows permuted
     size_t khat_bytes;
 };
 
@@ -79,8 +80,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int ND>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
-             const uint8_t* __restrict__ flags, const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
-             float* __restrict__ B_dyn) {
+             float* __restrict__ scratch) {
     typedef Cfg<ND> C;
     extern __shared__ __align__(128) unsigned char eb_smem[];
     __shared__ __align__(8) uint64_t bars[2];
@@ -130,7 +130,25 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         main_phase_accumulate<ND>(tid, kx0, np, Wb, tw, acc);
         __syncthreads();
     }
-    main_phase_write<ND>(tid, g, t, flags, E_stat, B_stat, E_dyn, B_dyn, acc);
+    main_phase_store<ND>(tid, g, t, scratch, acc);
+}
+
+// E_dyn = E_stat + KE * e, B_dyn = B_stat + KMU * b (sim.cl:986-992): one block per row (y, z), everything coalesced
+template <int ND>
+__global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom g, const float* __restrict__ scratch, const uint8_t* __restrict__ flags,
+                                                     const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
+                                                     float* __restrict__ B_dyn) {
+    extern __shared__ __align__(16) unsigned char eb_smem[];
+    float* tile = reinterpret_cast<float*>(eb_smem);  // [6][tile_len]
+    const uint32_t y = blockIdx.x, z = blockIdx.y;
+    if (((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u))) return;  // halo rows, sim.cl:899
+    const uint32_t tile_len = (g.nx / ND) * (ND + 1) + ND + 1;
+#pragma unroll
+    for (int c = 0; c < 6; c++) combine_load<ND>(threadIdx.x, blockDim.x, g, y, z, c, scratch, tile + (size_t)c * tile_len);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 6; c++)
+        combine_write<ND>(threadIdx.x, blockDim.x, g, y, z, c, tile + (size_t)c * tile_len, flags, E_stat, B_stat, E_dyn, B_dyn);
 }
 
 // The polyphase path needs: LOD depth 3 or 4, x and y extents that are whole LOD blocks (z may carry the two halo layers of a
@@ -190,6 +208,7 @@ void eb_fft_destroy(EbFftPlan* p) {
     if (p->tasks) cudaFree(p->tasks);
     if (p->khat) cudaFree(p->khat);
     if (p->shat) cudaFree(p->shat);
+    if (p->scratch) cudaFree(p->scratch);
     delete p;
 }
 
@@ -209,17 +228,19 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     if (!eb_fft_supported(a)) return cudaSuccess;
     EbFftPlan* p = new EbFftPlan();
     p->nd = 1 << a.lod_depth;
-    p->tasks = nullptr; p->khat = nullptr; p->shat = nullptr;
+    p->tasks = nullptr; p->khat = nullptr; p->shat = nullptr; p->scratch = nullptr;
     std::vector<Task> tasks;
     eb_fft_geometry(a, p->g, tasks);
     p->ntasks = (uint32_t)tasks.size();
     const size_t per = p->nd == 16 ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
     const size_t sh = p->nd == 16 ? Cfg<16>::shat_count : Cfg<8>::shat_count;
     p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
-    if (p->khat_bytes > budget_bytes) { delete p; return cudaSuccess; }
+    const size_t scratch_bytes = (size_t)6 * a.N * sizeof(float);
+    if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->khat, p->khat_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->shat, sh * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->scratch, scratch_bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `tasks` is a local vector
     if (e == cudaSuccess) e = p->nd == 16 ? build_khat<16>(p, s) : build_khat<8>(p, s);
@@ -238,14 +259,23 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     cudaError_t e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
     if (e != cudaSuccess) return e;
     k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, a.QU_lod, p->shat);
-    k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn);
+    k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->scratch);
+    const uint32_t tile_len = (a.nx / ND) * (ND + 1) + ND + 1;
+    const size_t csmem = (size_t)6 * tile_len * sizeof(float);
+    if (csmem > 48u * 1024u) {
+        e = cudaFuncSetAttribute(k_eb_combine<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
+        if (e != cudaSuccess) return e;
+    }
+    k_eb_combine<ND><<<dim3(a.ny, a.nz), a.nx < 256u ? ((a.nx + 31u) / 32u) * 32u : 256u, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn,
+                                                                                                       a.B_dyn);
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    *launches += 2;
+    *launches += 3;
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }
+size_t eb_fft_scratch_bytes(const EbFftPlan* p) { return p ? (size_t)6 * p->g.N * sizeof(float) : 0; }
 uint32_t eb_fft_plan_tasks(const EbFftPlan* p) { return p ? p->ntasks : 0; }
 
 }  // namespace ion

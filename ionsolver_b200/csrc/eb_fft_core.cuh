@@ -357,53 +357,52 @@ template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, co
         }
     }
 }
-// epilogue: sim.cl:986-992 for the cells of this task.  The cells of one task are ds apart, so every access is its own sector;
-// all loads of a group of x positions (flags, static fields) are issued before anything depends on them -- a loop that tests the
-// flag byte first and then loads costs two dependent HBM round trips per cell (it was 57 % of the kernel's stall samples).
-template <int ND>
-ION_HD void main_phase_write(int tid, const Geom& g, const Task t, const uint8_t* flags, const float* E_stat, const float* B_stat, float* E_dyn,
-                             float* B_dyn, const float (&acc)[6][Cfg<ND>::XPT]) {
+// Hand-over of a task's sums.  The cells of one task are ds apart in x (one cell per 64 bytes at ds = 16), so writing E_dyn / B_dyn
+// -- and reading flags, E_stat, B_stat -- from here would touch one 32-byte sector per 4-byte access: 53 000 sector operations per
+// task, measured as 60 % of the kernel.  Instead the sums go to a scratch field whose ROWS ARE PERMUTED: inside row (y, z) the value
+// of cell x = bx * ds + ox sits at ox * ND + bx, so a thread's ND block positions are contiguous (64 bytes, vector stores).
+// main_combine_row below undoes the permutation with fully coalesced traffic.  Layout: scratch[6][nz][ny][nx] floats.
+template <int ND> ION_HD void main_phase_store(int tid, const Geom& g, const Task t, float* scratch, const float (&acc)[6][Cfg<ND>::XPT]) {
     typedef Cfg<ND> C;
     constexpr int YZ = ND * ND;
-    constexpr int G = C::XPT < 4 ? C::XPT : 4;  // x positions per group
     const int yz = tid % YZ, xg = tid / YZ;
     const uint32_t y = (uint32_t)(yz % ND) * g.dsy + t.oy;
     const uint32_t z = ((uint32_t)(yz / ND) + (uint32_t)ND * t.wz) * g.dsz + t.oz;
     if (z >= g.nz || y >= g.ny) return;
-    const bool halo_yz = ((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u));
-    if (halo_yz) return;
-    const uint64_t row = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+    float* row = scratch + ((uint64_t)y + (uint64_t)z * g.ny) * g.nx + (uint64_t)t.ox * ND + (uint64_t)xg * C::XPT;
 #pragma unroll
-    for (int i0 = 0; i0 < C::XPT; i0 += G) {
-        uint64_t n[G];
-        bool live[G];
-        uint8_t fl[G];
-        float st[6][G];
+    for (int c = 0; c < 6; c++) {
+        float* p = row + (uint64_t)c * g.N;
+        if (C::XPT % 4 == 0) {
 #pragma unroll
-        for (int k = 0; k < G; k++) {
-            const uint32_t x = (uint32_t)(xg * C::XPT + i0 + k) * g.dsx + t.ox;
-            live[k] = x < g.nx && !((g.dx > 1u) & (x == 0u || x >= g.nx - 1u));  // is_halo, sim.cl:899
-            n[k] = row + (live[k] ? x : 0u);
+            for (int i = 0; i < C::XPT; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(acc[c][i], acc[c][i + 1], acc[c][i + 2], acc[c][i + 3]);
+        } else if (C::XPT % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < C::XPT; i += 2) *reinterpret_cast<float2*>(p + i) = make_float2(acc[c][i], acc[c][i + 1]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < C::XPT; i++) p[i] = acc[c][i];
         }
-#pragma unroll
-        for (int k = 0; k < G; k++) fl[k] = flags[n[k]];
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                st[c][k] = E_stat[(uint64_t)c * g.N + n[k]];
-                st[3 + c][k] = B_stat[(uint64_t)c * g.N + n[k]];
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < G; k++) {
-            if (!live[k] || (fl[k] & 0x1Fu) == 0x01u) continue;  // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
-                E_dyn[(uint64_t)c * g.N + n[k]] = st[c][k] + g.ke * acc[c][i0 + k];
-                B_dyn[(uint64_t)c * g.N + n[k]] = st[3 + c][k] + g.kmu * acc[3 + c][i0 + k];
-            }
-        }
+    }
+}
+// sim.cl:986-992 for one row (y, z): E_dyn = E_stat + KE * e, B_dyn = B_stat + KMU * b for every non-solid, non-halo cell.
+// `tile` holds the permuted row of one component, padded (ox * (ND + 1) + bx) so that the un-permuting reads are conflict-free.
+template <int ND>
+ION_HD void combine_load(int tid, int nthreads, const Geom& g, uint32_t y, uint32_t z, int c, const float* scratch, float* tile) {
+    const float* row = scratch + (uint64_t)c * g.N + ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+    for (uint32_t i = tid; i < g.nx; i += nthreads) tile[(i / ND) * (ND + 1) + i % ND] = row[i];
+}
+template <int ND>
+ION_HD void combine_write(int tid, int nthreads, const Geom& g, uint32_t y, uint32_t z, int c, const float* tile, const uint8_t* flags,
+                          const float* E_stat, const float* B_stat, float* E_dyn, float* B_dyn) {
+    const uint64_t base = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+    const float* stat = (c < 3 ? E_stat : B_stat) + (uint64_t)(c % 3) * g.N + base;
+    float* dyn = (c < 3 ? E_dyn : B_dyn) + (uint64_t)(c % 3) * g.N + base;
+    const float k = c < 3 ? g.ke : g.kmu;
+    for (uint32_t x = tid; x < g.nx; x += nthreads) {
+        if ((g.dx > 1u) & (x == 0u || x >= g.nx - 1u)) continue;  // is_halo, sim.cl:899
+        if ((flags[base + x] & 0x1Fu) == 0x01u) continue;         // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
+        dyn[x] = stat[x] + k * tile[(x % g.dsx) * (ND + 1) + x / g.dsx];
     }
 }
 

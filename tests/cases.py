@@ -148,6 +148,24 @@ def fill_drift_inputs(lbm, cfg, seed=21):
         d.b_stat[:] = 0
 
 
+def taylor_green_numpy(n):
+    """setup.rs:458-543 in numpy float32 (one domain)."""
+    f32 = np.float32
+    pif, A = f32(np.pi), f32(0.25)
+    g = np.arange(n, dtype=np.float32)
+    f = (g + f32(0.5) - f32(0.5) * f32(n)).astype(np.float32)
+    a = f32(n)
+    arg2 = (f32(2.0) * pif * f / a).astype(np.float32)
+    arg4 = (f32(4.0) * pif * f / a).astype(np.float32)
+    c2, s2, c4 = np.cos(arg2), np.sin(arg2), np.cos(arg4)
+    Z, Y, X = np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing="ij")
+    ux = A * c2[X] * s2[Y] * s2[Z]
+    uy = -A * s2[X] * c2[Y] * s2[Z]
+    uz = A * s2[X] * s2[Y] * c2[Z]
+    rho = f32(1.0) - (A * A) * f32(3.0) / f32(4.0) * c4[X] + c4[Y]
+    return np.concatenate([ux.ravel(), uy.ravel(), uz.ravel()]).astype(np.float32), rho.ravel().astype(np.float32)
+
+
 def _ecr(c, length=16.0):
     """Units for the SUBGRID_ECR cases.  The extension is experimental in the reference (sim.cl:556-629: debug printfs, a
     placeholder ionisation term, `a - b / 2.0f` in grad_mag_v) and with setup_deeva_test's units DEF_KKBME is ~ -1e12, so the

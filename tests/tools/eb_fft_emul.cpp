@@ -63,6 +63,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     for (auto& v : Bs) v = U(rng);
     flags[5 + 7 * nx + 9 * nx * ny] = 0x01;  // one solid cell: must stay untouched
     std::vector<float2> W((size_t)C::P * C::PLANE), tw(C::M);
+    std::vector<float> scratch((size_t)6 * g.N, 0.0f);
     for (int i = 0; i < C::M; i++) tw[i] = make_float2(tw_cos32(i * (32 / C::M)), tw_sin32(i * (32 / C::M)));
     std::vector<float> accreg((size_t)C::T * 6 * C::XPT);
     for (int t = 0; t < ntasks; t++) {
@@ -78,8 +79,19 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
                 main_phase_accumulate<ND>(tid, kx0, np, W.data(), tw.data(), *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
         }
         for (int tid = 0; tid < C::T; tid++)
-            main_phase_write<ND>(tid, g, tasks[t], flags.data(), Es.data(), Bs.data(), Ed.data(), Bd.data(),
-                                 *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
+            main_phase_store<ND>(tid, g, tasks[t], scratch.data(), *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
+    }
+    {  // k_eb_combine: one block per row
+        std::vector<float> tile((size_t)(nx / ND) * (ND + 1) + ND + 1);
+        for (uint32_t z = 0; z < nz; z++)
+            for (uint32_t y = 0; y < ny; y++) {
+                if (dz > 1 && (z == 0 || z >= nz - 1)) continue;
+                for (int c = 0; c < 6; c++) {
+                    for (int tid = 0; tid < 128; tid++) combine_load<ND>(tid, 128, g, y, z, c, scratch.data(), tile.data());
+                    for (int tid = 0; tid < 128; tid++)
+                        combine_write<ND>(tid, 128, g, y, z, c, tile.data(), flags.data(), Es.data(), Bs.data(), Ed.data(), Bd.data());
+                }
+            }
     }
     // direct reference (double), reference semantics
     double num[2] = {0, 0}, den[2] = {0, 0}, maxerr = 0;
