@@ -236,7 +236,18 @@ class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self.stop, self.source = [], set(), None, threading.Event(), "nvidia-smi"
         self.index = index
+        self.window = [None, None]  # perf_counter bounds of the timed region; the sampler itself starts before the warm-up
         self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def begin(self):
+        self.window[0] = time.perf_counter()
+
+    def end(self):
+        self.window[1] = time.perf_counter()
+
+    def _record(self, mhz, reasons):
+        now = time.perf_counter()
+        self.samples.append((now, mhz, tuple(reasons)))
 
     def _run(self):
         if self._run_nvml():
@@ -248,11 +259,8 @@ class ClockSampler:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip().split(",")
-                self.samples.append(float(out[0]))
                 self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
-                    if v.strip().lower().startswith("active"):
-                        self.reasons.add(n)
+                self._record(float(out[0]), [n for n, v in zip(names, out[2:]) if v.strip().lower().startswith("active")])
             except Exception:
                 pass
             self.stop.wait(0.1)
@@ -275,14 +283,12 @@ class ClockSampler:
         self.source = "nvml"
         while not self.stop.is_set():
             try:
-                self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                mhz = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 r = int(get_reasons(h))
-                for b, n in bits.items():
-                    if r & b:
-                        self.reasons.add(n)
+                self._record(mhz, [n for b, n in bits.items() if r & b])
             except Exception:
                 pass
-            self.stop.wait(0.005)
+            self.stop.wait(0.002)
         return True
 
     def __enter__(self):
@@ -294,9 +300,13 @@ class ClockSampler:
         self.thread.join(timeout=6)
 
     def summary(self):
-        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "sm_mhz_min": float(np.min(self.samples)) if self.samples else None,
-                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
+        t0, t1 = self.window
+        inside = [s for s in self.samples if t0 is not None and t1 is not None and t0 <= s[0] <= t1]
+        use = inside or self.samples  # a timed region shorter than one sampling period: fall back to everything sampled under load
+        mhz = [s[1] for s in use]
+        reasons = sorted({r for s in use for r in s[2]})
+        return {"sm_mhz": float(np.median(mhz)) if mhz else None, "sm_max_mhz": self.max_mhz, "sm_mhz_min": float(np.min(mhz)) if mhz else None,
+                "reasons": reasons, "samples": len(use), "samples_inside_timed_region": len(inside), "source": self.source}
 
 
 def make_lbm(L, cfg_l, rank, world, device):
@@ -453,11 +463,14 @@ def run_ours(args, rank, world, local_rank):
         return ms
 
     # ---- whole-step throughput, inputs resident in HBM ----
-    for _ in range(max(args.warmup, 3)):
-        lbm.do_time_step()
-    with ClockSampler(device) as clocks:
+    with ClockSampler(device) as clocks:  # started before the warm-up so that NVML is initialised when the timed region begins
+        for _ in range(max(args.warmup, 3)):
+            lbm.do_time_step()
+        barrier()
         l0 = capi.kernel_launch_count()
+        clocks.begin()
         ms_total = timed(lbm.do_time_step, args.steps)
+        clocks.end()
         launches = capi.kernel_launch_count() - l0
     ms_step = ms_total / args.steps
     value = cells_global / (ms_step * 1e-3) / 1e6

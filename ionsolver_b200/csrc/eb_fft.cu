@@ -18,29 +18,37 @@ struct EbFftPlan {
     int nd;
     uint32_t ntasks;
     Geom g;
+    // source sets summed by FFT: [0] the own finest level, [1] (z slabs with a lower neighbour) that neighbour's level D-1 pyramid
+    int nsets;
+    SourceSet sets[2];
+    int foreign_domain;  // domain index whose pyramid is set 1, -1 = none (the direct kernel must then sum it)
     Task* tasks;
-    float2* khat;
+    float2* khat;   // nsets * ntasks * khat_per_task
     float2* shat;
     float* scratch;  // the sums of a step before they are combined with the static fields: 6 floats per cell, rows permuted
     size_t khat_bytes;
 };
 
-template <int ND> __global__ void __launch_bounds__(256) k_eb_khat(const __grid_constant__ Geom g, const Task* __restrict__ tasks, float2* __restrict__ khat) {
-    extern __shared__ __align__(16) unsigned char eb_smem[];
+template <int ND>
+__global__ void __launch_bounds__(256) k_eb_khat(const __grid_constant__ Geom g, const __grid_constant__ SourceSet ss, const Task* __restrict__ tasks,
+                                                  float2* __restrict__ khat) {
+    extern __shared__ __align__(128) unsigned char eb_smem[];
     float2* S = reinterpret_cast<float2*>(eb_smem);
     const int task = blockIdx.x, comp = blockIdx.y;
     const Task t = tasks[task];
-    khat_phase_x<ND>(threadIdx.x, blockDim.x, g, t, comp, S);
+    khat_phase_x<ND>(threadIdx.x, blockDim.x, g, ss, t, comp, S);
     __syncthreads();
     khat_phase_y<ND>(threadIdx.x, blockDim.x, S);
     __syncthreads();
     khat_phase_z<ND>(threadIdx.x, blockDim.x, task, comp, S, khat);
 }
 
-template <int ND> __global__ void __launch_bounds__(128) k_eb_src(const __grid_constant__ Geom g, const float* __restrict__ QU_lod, float2* __restrict__ shat) {
+template <int ND>
+__global__ void __launch_bounds__(128) k_eb_src(const __grid_constant__ Geom g, const __grid_constant__ SourceSet ss, const float* __restrict__ QU_lod,
+                                                 float2* __restrict__ shat) {
     __shared__ float2 plane[Cfg<ND>::M * Cfg<ND>::ROW];
     const int kx = blockIdx.x, j = blockIdx.y;
-    src_phase_x<ND>(threadIdx.x, blockDim.x, g, QU_lod, kx, j, plane);
+    src_phase_x<ND>(threadIdx.x, blockDim.x, g, ss, QU_lod, kx, j, plane);
     __syncthreads();
     src_phase_y<ND>(threadIdx.x, blockDim.x, plane);
     __syncthreads();
@@ -80,12 +88,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int ND>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
-             float* __restrict__ scratch) {
+             float* __restrict__ scratch, const int accumulate) {
     typedef Cfg<ND> C;
     extern __shared__ __align__(128) unsigned char eb_smem[];
     __shared__ __align__(8) uint64_t bars[2];
     float2* W = reinterpret_cast<float2*>(eb_smem);  // [2][P][6][M][ROW]
-    float2* tw = W + (size_t)2 * C::P * C::PLANE;
+    float2* S0 = W + (size_t)2 * C::P * C::PLANE;     // s^_0 of the current planes [P][M][ROW] (single buffer, see below)
+    float2* tw = S0 + (size_t)C::P * C::SLOT;
     const int tid = threadIdx.x;
     if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
     const Task t = tasks[blockIdx.x];
@@ -96,19 +105,23 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto stage = [&](int it) {  // thread 0: K^ of iteration `it` -> E slots, s^_1..3 -> B slots of buffer it & 1
+    // thread 0: operands of iteration `it` -> buffer it & 1: K^ into the E slots, s^_1..3 into the B slots, s^_0 into S0
+    auto stage = [&](int it) {
         const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the buffer was last touched by ordinary loads / stores
-        mbar_expect_tx(&bars[it & 1], (uint32_t)(np * 6 * C::SLOT * sizeof(float2)));
-        for (int p = 0; p < np; p++)
+        uint64_t* bar = &bars[it & 1];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the targets were last touched by ordinary loads / stores
+        mbar_expect_tx(bar, (uint32_t)(np * 7 * C::SLOT * sizeof(float2)));
+        for (int p = 0; p < np; p++) {
+            bulk_g2s(S0 + (size_t)p * C::SLOT, shat + ((size_t)kx0 + p) * C::SLOT, (uint32_t)(C::SLOT * sizeof(float2)), bar);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)c * C::SLOT, kt + ((size_t)c * C::H + kx0 + p) * C::SLOT,
-                         (uint32_t)(C::SLOT * sizeof(float2)), &bars[it & 1]);
+                         (uint32_t)(C::SLOT * sizeof(float2)), bar);
                 bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT, shat + ((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT,
-                         (uint32_t)(C::SLOT * sizeof(float2)), &bars[it & 1]);
+                         (uint32_t)(C::SLOT * sizeof(float2)), bar);
             }
+        }
     };
     if (tid == 0) stage(0);
     float acc[6][C::XPT];
@@ -119,36 +132,85 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     for (int it = 0; it < C::NIT; it++) {
         const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
-        if (tid == 0 && it + 1 < C::NIT) stage(it + 1);  // the other buffer is idle since the barrier that closed iteration it - 1
         mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-        main_phase_product<ND>(tid, shat, kx0, np, Wb);
+        main_phase_product<ND>(tid, S0, np, Wb);
         __syncthreads();
+        // Every thread is past the x accumulation of iteration it - 1 (which read the other buffer) and past this iteration's
+        // products (which read S0): both are free, the operands of iteration it + 1 can land while this one is transformed.
+        if (tid == 0 && it + 1 < C::NIT) stage(it + 1);
         main_phase_z<ND>(tid, np, Wb);
         __syncthreads();
         main_phase_y<ND>(tid, np, Wb);
         __syncthreads();
-        main_phase_accumulate<ND>(tid, kx0, np, Wb, tw, acc);
-        __syncthreads();
+        main_phase_accumulate<ND>(tid, kx0, np, Wb, tw, acc);  // no barrier: the next iteration works on the other buffer
     }
-    main_phase_store<ND>(tid, g, t, scratch, acc);
+    main_phase_store<ND>(tid, g, t, scratch, accumulate != 0, acc);
 }
 
-// E_dyn = E_stat + KE * e, B_dyn = B_stat + KMU * b (sim.cl:986-992): one block per row (y, z), everything coalesced
-template <int ND>
+// E_dyn = E_stat + KE * e, B_dyn = B_stat + KMU * b (sim.cl:986-992): one block per row (y, z), everything coalesced.  A thread
+// owns CH cells of the row (x = threadIdx.x + k * blockDim.x); all 13 loads per cell (6 scratch components, flag, 6 static
+// components) are in flight before the first is used; the scratch values pass through shared memory, which undoes the row
+// permutation (combine_load / combine_write of eb_fft_core.cuh are the per-component form of the same thing, used by the CPU
+// emulation).  CH = 0: rows longer than 8 * blockDim, static fields loaded after the barrier instead of being kept in registers.
+template <int ND, int CH>
 __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom g, const float* __restrict__ scratch, const uint8_t* __restrict__ flags,
                                                      const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
                                                      float* __restrict__ B_dyn) {
-    extern __shared__ __align__(16) unsigned char eb_smem[];
+    extern __shared__ __align__(128) unsigned char eb_smem[];
     float* tile = reinterpret_cast<float*>(eb_smem);  // [6][tile_len]
     const uint32_t y = blockIdx.x, z = blockIdx.y;
     if (((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u))) return;  // halo rows, sim.cl:899
     const uint32_t tile_len = (g.nx / ND) * (ND + 1) + ND + 1;
+    const uint64_t base = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+    constexpr int R = CH > 0 ? CH : 1;
+    float st[R][6];
+    uint8_t fl[R];
+    if (CH > 0) {
+        float sv[R][6];
 #pragma unroll
-    for (int c = 0; c < 6; c++) combine_load<ND>(threadIdx.x, blockDim.x, g, y, z, c, scratch, tile + (size_t)c * tile_len);
+        for (int k = 0; k < R; k++) {
+            const uint32_t x = threadIdx.x + (uint32_t)k * blockDim.x;
+            fl[k] = 0x01;
+            if (x < g.nx) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) sv[k][c] = scratch[(uint64_t)c * g.N + base + x];
+                fl[k] = flags[base + x];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    st[k][c] = E_stat[(uint64_t)c * g.N + base + x];
+                    st[k][3 + c] = B_stat[(uint64_t)c * g.N + base + x];
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < R; k++) {
+            const uint32_t x = threadIdx.x + (uint32_t)k * blockDim.x;
+            if (x < g.nx) {
+#pragma unroll
+                for (int c = 0; c < 6; c++) tile[(size_t)c * tile_len + (x / ND) * (ND + 1) + x % ND] = sv[k][c];
+            }
+        }
+    } else {
+        for (int c = 0; c < 6; c++) combine_load<ND>(threadIdx.x, blockDim.x, g, y, z, c, scratch, tile + (size_t)c * tile_len);
+    }
     __syncthreads();
+    if (CH > 0) {
 #pragma unroll
-    for (int c = 0; c < 6; c++)
-        combine_write<ND>(threadIdx.x, blockDim.x, g, y, z, c, tile + (size_t)c * tile_len, flags, E_stat, B_stat, E_dyn, B_dyn);
+        for (int k = 0; k < R; k++) {
+            const uint32_t x = threadIdx.x + (uint32_t)k * blockDim.x;
+            if (x >= g.nx || ((g.dx > 1u) & (x == 0u || x >= g.nx - 1u))) continue;  // is_halo, sim.cl:899
+            if ((fl[k] & 0x1Fu) == 0x01u) continue;                                   // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
+            const uint32_t p = (x % g.dsx) * (ND + 1) + x / g.dsx;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                E_dyn[(uint64_t)c * g.N + base + x] = st[k][c] + g.ke * tile[(size_t)c * tile_len + p];
+                B_dyn[(uint64_t)c * g.N + base + x] = st[k][3 + c] + g.kmu * tile[(size_t)(3 + c) * tile_len + p];
+            }
+        }
+    } else {
+        for (int c = 0; c < 6; c++)
+            combine_write<ND>(threadIdx.x, blockDim.x, g, y, z, c, tile + (size_t)c * tile_len, flags, E_stat, B_stat, E_dyn, B_dyn);
+    }
 }
 
 // The polyphase path needs: LOD depth 3 or 4, x and y extents that are whole LOD blocks (z may carry the two halo layers of a
@@ -217,8 +279,33 @@ template <int ND> static cudaError_t build_khat(EbFftPlan* p, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
     if (e != cudaSuccess) return e;
-    k_eb_khat<ND><<<dim3(p->ntasks, 3), 256, Cfg<ND>::khat_smem, s>>>(p->g, p->tasks, p->khat);
+    for (int set = 0; set < p->nsets; set++)
+        k_eb_khat<ND><<<dim3(p->ntasks, 3), 256, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task);
     return cudaGetLastError();
+}
+
+// Second source set: the level D-1 pyramid of the z slab directly below (domain di - 1; slabs above sit ~4.29e9 cells away through
+// the uint wrap of quirk Q18 and are skipped by the fast paths).  It convolves on the own block lattice when its blocks are exactly
+// two own blocks wide on every axis; `entry0` follows the layout of mod.rs:448-465 (foreign levels appended in ascending domain
+// index, self skipped).
+static void foreign_set(const KArgs& a, const Geom& g, EbFftPlan* p) {
+    p->foreign_domain = -1;
+    if (a.dx != 1u || a.dy != 1u || a.dz < 2u || a.di == 0u || a.lod_depth < 1u) return;
+    if (a.dz - 1u > 32u) return;  // the direct kernel cannot address single foreign domains any more (MAX_FOREIGN in fields.cu)
+    const uint32_t nd = 1u << a.lod_depth, nf = nd / 2u;
+    if (a.nx / nf != 2u * g.dsx || a.ny / nf != 2u * g.dsy || a.nz / nf != 2u * g.dsz) return;
+    uint32_t entry = a.n_lod_own;
+    for (uint32_t d = 0; d + 1u < a.di; d++) {  // levels of the domains below the neighbour: max(depth - distance, 0)
+        const int level = (int)a.lod_depth - (int)(a.di - d) > 0 ? (int)a.lod_depth - (int)(a.di - d) : 0;
+        entry += 1u << (3 * level);
+    }
+    SourceSet& ss = p->sets[1];
+    ss.kind = 1u;
+    ss.entry0 = entry;
+    ss.zadd = (int32_t)(a.nz / g.dsz);  // slab height incl. halos = zadd * dsz + offz (quirk Q8)
+    ss.offx = 0.0f; ss.offy = 0.0f; ss.offz = (float)(a.nz % g.dsz);
+    p->nsets = 2;
+    p->foreign_domain = (int)a.di - 1;
 }
 
 // Builds the static part (task list, K^) on the domain's device.  *out = nullptr (and cudaSuccess) when the geometry is not
@@ -232,10 +319,18 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     std::vector<Task> tasks;
     eb_fft_geometry(a, p->g, tasks);
     p->ntasks = (uint32_t)tasks.size();
+    p->nsets = 1;
+    p->sets[0] = SourceSet{0u, 0u, -(int32_t)p->g.cz0, -0.5f * (float)p->g.dsx, -0.5f * (float)p->g.dsy, -0.5f * (float)p->g.dsz};
+    foreign_set(a, p->g, p);
     const size_t per = p->nd == 16 ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
     const size_t sh = p->nd == 16 ? Cfg<16>::shat_count : Cfg<8>::shat_count;
-    p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
     const size_t scratch_bytes = (size_t)6 * a.N * sizeof(float);
+    p->khat_bytes = (size_t)p->nsets * p->ntasks * per * sizeof(float2);
+    if (p->nsets == 2 && p->khat_bytes + scratch_bytes > budget_bytes) {  // no room for the neighbour's spectra: direct kernel for it
+        p->nsets = 1;
+        p->foreign_domain = -1;
+        p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
+    }
     if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->khat, p->khat_bytes);
@@ -249,7 +344,7 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
         if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return cudaSuccess; }  // no room: the direct kernels stay in charge
         return e;
     }
-    (*launches)++;
+    *launches += (uint64_t)p->nsets;
     *out = p;
     return cudaSuccess;
 }
@@ -258,23 +353,38 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     // function attributes are per device: set on every launch (a host-side table lookup)
     cudaError_t e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
     if (e != cudaSuccess) return e;
-    k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, a.QU_lod, p->shat);
-    k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->scratch);
+    for (int set = 0; set < p->nsets; set++) {  // the source spectrum buffer is reused: the launches are ordered on the stream
+        k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat);
+        k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task, p->shat,
+                                                                        p->scratch, set);
+    }
     const uint32_t tile_len = (a.nx / ND) * (ND + 1) + ND + 1;
     const size_t csmem = (size_t)6 * tile_len * sizeof(float);
-    if (csmem > 48u * 1024u) {
-        e = cudaFuncSetAttribute(k_eb_combine<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
-        if (e != cudaSuccess) return e;
-    }
-    k_eb_combine<ND><<<dim3(a.ny, a.nz), a.nx < 256u ? ((a.nx + 31u) / 32u) * 32u : 256u, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn,
-                                                                                                       a.B_dyn);
+    const uint32_t threads = a.nx < 256u ? ((a.nx + 31u) / 32u) * 32u : 256u;
+    const uint32_t chunks = (a.nx + threads - 1u) / threads;
+    const dim3 grid(a.ny, a.nz);
+#define ION_COMBINE(CH)                                                                                                          \
+    do {                                                                                                                           \
+        if (csmem > 48u * 1024u) {                                                                                                 \
+            e = cudaFuncSetAttribute(k_eb_combine<ND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);               \
+            if (e != cudaSuccess) return e;                                                                                        \
+        }                                                                                                                          \
+        k_eb_combine<ND, CH><<<grid, threads, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn);         \
+    } while (0)
+    if (chunks <= 1u) ION_COMBINE(1);
+    else if (chunks <= 2u) ION_COMBINE(2);
+    else if (chunks <= 4u) ION_COMBINE(4);
+    else if (chunks <= 8u) ION_COMBINE(8);
+    else ION_COMBINE(0);
+#undef ION_COMBINE
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    *launches += 3;
+    *launches += 1u + 2u * (uint64_t)p->nsets;
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }
+int eb_fft_plan_foreign_domain(const EbFftPlan* p) { return p ? p->foreign_domain : -1; }
 size_t eb_fft_scratch_bytes(const EbFftPlan* p) { return p ? (size_t)6 * p->g.N * sizeof(float) : 0; }
 uint32_t eb_fft_plan_tasks(const EbFftPlan* p) { return p ? p->ntasks : 0; }
 

@@ -48,6 +48,18 @@ struct Geom {
     uint32_t dx, dy, dz;     // domain grid (halo test, sim.cl:145-148)
     float ke, kmu;
 };
+// A set of sources that sits on the block lattice and therefore convolves: r = ds * (block difference) + (o + off).
+//   kind 0: the own finest level, window [lo, n_lod_own) of sim.cl:943, positions from the table index (quirk Q5): centre
+//           (c + 1/2) ds, i.e. off = -ds/2; z rows start at cz0, i.e. zadd = -cz0; the cell's own block is skipped (sim.cl:944).
+//   kind 1: the level D-1 pyramid of the slab below (sim.cl:957-983).  Its blocks are two own blocks wide, centre (2i + 1) ds:
+//           the source lands on the ODD positions of the ND-grid with off = 0 in x, y; in z the centre is shifted by the slab
+//           height INCLUDING halos (quirk Q8), nz = A dsz + B: zadd = A, off_z = B.  No self-skip.
+struct SourceSet {
+    uint32_t kind;
+    uint32_t entry0;  // kind 1: first QU_lod entry of the neighbour's pyramid level
+    int32_t zadd;     // true z block difference = circular difference + ND * wz + zadd
+    float offx, offy, offz;
+};
 // one polyphase problem: the cells (b*ds + o) with z blocks [ND*wz, ND*wz + ND)
 struct Task {
     uint16_t ox, oy, oz, wz;
@@ -57,16 +69,20 @@ template <int ND> struct Cfg {
     static constexpr int M = 2 * ND;      // FFT length per axis
     static constexpr int H = ND + 1;      // Hermitian half: kx = 0..ND
     static constexpr int ROW = M + 1;     // padded row of the shared-memory planes (bank-conflict-free strided access)
-    static constexpr int T = 256;         // threads of the main kernel (x accumulators live in registers: 6 * XPT per thread)
     static constexpr int P = ND == 16 ? 2 : 3;  // kx planes per iteration; the kernel holds two such groups (double buffer)
     static constexpr int NIT = (H + P - 1) / P; // iterations per task
-    static constexpr int XG = T / (ND * ND);    // thread groups along x in the accumulation phase
-    static constexpr int XPT = ND / XG;         // x outputs per thread
+    // threads of the main kernel.  ND = 16: 384 = P * 6 spectra * 32 columns, so the z pass is exactly one FFT per thread (12 warps,
+    // one (plane, spectrum) each); the y pass uses half of them and the x accumulation the first 256 (one per (y, z) point)
+    static constexpr int T = ND == 16 ? 384 : 256;
+    static constexpr int XG = ND == 16 ? 1 : 4; // thread groups along x in the accumulation phase (ND^2 * XG threads take part)
+    static constexpr int XPT = ND / XG;         // x outputs per thread (they live in registers: 6 * XPT accumulators)
+    static constexpr int TACC = ND * ND * XG;   // threads that own accumulators
     static constexpr int PLANE = 6 * M * ROW;   // float2 per kx plane: E^x E^y E^z B^x B^y B^z
     static constexpr int SLOT = M * ROW;        // float2 per (spectrum, kx) slot; K^ and s^ use the same padded rows in HBM
     static constexpr size_t khat_per_task = (size_t)3 * H * SLOT;  // float2
     static constexpr size_t shat_count = (size_t)4 * H * SLOT;     // float2
-    static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + M * sizeof(float2);
+    // work buffers [2][P][6 slots] + s^_0 staging [P slots] + x twiddles
+    static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + (size_t)P * SLOT * sizeof(float2) + M * sizeof(float2);
     static constexpr size_t khat_smem = (size_t)H * M * ROW * sizeof(float2);
     static constexpr size_t src_smem = (size_t)M * ROW * sizeof(float2);
 };
@@ -156,23 +172,23 @@ ION_HD float2 cmul_sub(float2 a, float2 b, float2 c, float2 d) {
 // signed block difference of circular index m
 template <int ND> ION_HD int circ_diff(int m) { return m < ND ? m : m - 2 * ND; }
 
-template <int ND> ION_HD void khat_phase_x(int tid, int nthreads, const Geom& g, const Task t, int comp, float2* S) {
+template <int ND> ION_HD void khat_phase_x(int tid, int nthreads, const Geom& g, const SourceSet& ss, const Task t, int comp, float2* S) {
     typedef Cfg<ND> C;
     for (int line = tid; line < C::M * C::M; line += nthreads) {
         const int mz = line / C::M, my = line % C::M;
         const int ddy = circ_diff<ND>(my);
-        const int ddz = circ_diff<ND>(mz) + ND * (int)t.wz - (int)g.cz0;  // true block difference along z
+        const int ddz = circ_diff<ND>(mz) + ND * (int)t.wz + ss.zadd;  // true block difference along z
         // r = (float)cell - ((float)c * ds + 0.5 ds): small integers and half-integers, exact in any precision (sim.cl:945, :440-447)
-        const double ry = (double)ddy * g.dsy + ((double)t.oy - 0.5 * g.dsy);
-        const double rz = (double)ddz * g.dsz + ((double)t.oz - 0.5 * g.dsz);
+        const double ry = (double)ddy * g.dsy + ((double)t.oy + (double)ss.offy);
+        const double rz = (double)ddz * g.dsz + ((double)t.oz + (double)ss.offz);
         float2 a[C::M];
 #pragma unroll
         for (int mx = 0; mx < C::M; mx++) {
             const int ddx = circ_diff<ND>(mx);
-            const double rx = (double)ddx * g.dsx + ((double)t.ox - 0.5 * g.dsx);
+            const double rx = (double)ddx * g.dsx + ((double)t.ox + (double)ss.offx);
             const double r2 = rx * rx + ry * ry + rz * rz;
             double k = 0.0;
-            if (!(ddx == 0 && ddy == 0 && ddz == 0) && r2 > 0.0) {  // the cell's own block contributes nothing (sim.cl:944)
+            if (!(ss.kind == 0u && ddx == 0 && ddy == 0 && ddz == 0) && r2 > 0.0) {  // the cell's own block contributes nothing (sim.cl:944)
                 const double inv = 1.0 / (r2 * sqrt(r2));
                 k = (comp == 0 ? rx : comp == 1 ? ry : rz) * inv;
             }
@@ -220,20 +236,27 @@ template <int ND> ION_HD void khat_phase_z(int tid, int nthreads, int task, int 
 // ------------------------------------------------------------------------------------------------------
 // s^ of the source table: grid (H, 4), any thread count, shared plane[M][ROW].  Component j: q, q vx, q vy, q vz
 // ------------------------------------------------------------------------------------------------------
-template <int ND> ION_HD float src_value(const Geom& g, const float* QU_lod, int j, int cx, int cy, int czp) {
-    const uint32_t d = (uint32_t)cx + (uint32_t)ND * ((uint32_t)cy + (uint32_t)ND * ((uint32_t)czp + g.cz0));
-    if (d < g.lo || d >= g.n_lod_own) return 0.0f;  // outside the window of sim.cl:943
+template <int ND> ION_HD float src_value(const Geom& g, const SourceSet& ss, const float* QU_lod, int j, int cx, int cy, int czp) {
+    uint32_t d;
+    if (ss.kind == 0u) {
+        d = (uint32_t)cx + (uint32_t)ND * ((uint32_t)cy + (uint32_t)ND * ((uint32_t)czp + g.cz0));
+        if (d < g.lo || d >= g.n_lod_own) return 0.0f;  // outside the window of sim.cl:943
+    } else {  // entry (i, j, k) of the neighbour's level D-1 sits at (2i+1, 2j+1, 2k+1)
+        constexpr int NF = ND / 2;
+        if (!(cx & 1) || !(cy & 1) || !(czp & 1) || czp >= ND) return 0.0f;
+        d = ss.entry0 + (uint32_t)(cx >> 1) + (uint32_t)NF * ((uint32_t)(cy >> 1) + (uint32_t)NF * (uint32_t)(czp >> 1));
+    }
     const float q = QU_lod[4u * d];
     return j == 0 ? q : QU_lod[4u * d + (uint32_t)j] * q;
 }
-template <int ND> ION_HD void src_phase_x(int tid, int nthreads, const Geom& g, const float* QU_lod, int kx, int j, float2* plane) {
+template <int ND> ION_HD void src_phase_x(int tid, int nthreads, const Geom& g, const SourceSet& ss, const float* QU_lod, int kx, int j, float2* plane) {
     typedef Cfg<ND> C;
     for (int idx = tid; idx < (ND + 1) * ND; idx += nthreads) {
         const int czp = idx / ND, cy = idx % ND;
         float re = 0.0f, im = 0.0f;
 #pragma unroll
         for (int cx = 0; cx < ND; cx++) {
-            const float v = src_value<ND>(g, QU_lod, j, cx, cy, czp);
+            const float v = src_value<ND>(g, ss, QU_lod, j, cx, cy, czp);
             const int ti = ((kx * cx) % C::M) * (32 / C::M);
             re = fmaf(v, tw_cos32(ti), re);
             im = fmaf(v, -tw_sin32(ti), im);
@@ -278,27 +301,30 @@ template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, 
 
 // phase 0 (CPU emulation of what the kernel does with cp.async.bulk): the K^ slots of planes kx0 .. kx0+np-1 land in the E
 // slots (0..2) of the work buffer and the s^_1..3 slots (q vx, q vy, q vz) in the B slots (3..5)
-template <int ND> inline void main_stage_host(const float2* khat_task, const float2* shat, int kx0, int np, float2* W) {
+template <int ND> inline void main_stage_host(const float2* khat_task, const float2* shat, int kx0, int np, float2* W, float2* S0) {
     typedef Cfg<ND> C;
-    for (int p = 0; p < np; p++)
+    for (int p = 0; p < np; p++) {
+        for (int i = 0; i < C::SLOT; i++) S0[(size_t)p * C::SLOT + i] = shat[((size_t)kx0 + p) * C::SLOT + i];
         for (int c = 0; c < 3; c++)
             for (int i = 0; i < C::SLOT; i++) {
                 W[(size_t)p * C::PLANE + (size_t)c * C::SLOT + i] = khat_task[((size_t)c * C::H + kx0 + p) * C::SLOT + i];
                 W[(size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT + i] = shat[((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT + i];
             }
+    }
 }
 // phase 1: frequency-domain products of planes kx0 .. kx0+np-1, IN PLACE: the point's K^ (E slots) and s^_1..3 (B slots) are
-// read from where the bulk copies put them, s^_0 comes from L2, and the six products overwrite the same point of the six slots.
-template <int ND> ION_HD void main_phase_product(int tid, const float2* shat, int kx0, int np, float2* W) {
+// read from where the bulk copies put them, s^_0 from its own staging slots S0, and the six products overwrite the same point of
+// the six slots.
+template <int ND> ION_HD void main_phase_product(int tid, const float2* S0, int np, float2* W) {
     typedef Cfg<ND> C;
     constexpr int MM = C::M * C::M;
-#pragma unroll 8
+#pragma unroll 2
     for (int idx = tid; idx < np * MM; idx += C::T) {
         const int p = idx / MM, f = idx % MM;
         const int kz = f / C::M, ky = f % C::M;
         const int o = kz * C::ROW + ky;
         float2* w = W + (size_t)p * C::PLANE + o;
-        const float2 s0 = ION_LDG2(shat + (size_t)(kx0 + p) * C::SLOT + o);
+        const float2 s0 = S0[(size_t)p * C::SLOT + o];
         const float2 k0 = w[0], k1 = w[C::SLOT], k2 = w[2 * C::SLOT];
         const float2 s1 = w[3 * C::SLOT], s2 = w[4 * C::SLOT], s3 = w[5 * C::SLOT];
         w[0] = cmul(k0, s0);
@@ -341,6 +367,7 @@ template <int ND> ION_HD void main_phase_y(int tid, int np, float2* W) {
 template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, const float2* W, const float2* tw, float (&acc)[6][Cfg<ND>::XPT]) {
     typedef Cfg<ND> C;
     constexpr int YZ = ND * ND;
+    if (tid >= C::TACC) return;
     const int yz = tid % YZ, xg = tid / YZ;
     const int y = yz % ND, z = yz / ND;
     for (int p = 0; p < np; p++) {
@@ -362,9 +389,10 @@ template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, co
 // task, measured as 60 % of the kernel.  Instead the sums go to a scratch field whose ROWS ARE PERMUTED: inside row (y, z) the value
 // of cell x = bx * ds + ox sits at ox * ND + bx, so a thread's ND block positions are contiguous (64 bytes, vector stores).
 // main_combine_row below undoes the permutation with fully coalesced traffic.  Layout: scratch[6][nz][ny][nx] floats.
-template <int ND> ION_HD void main_phase_store(int tid, const Geom& g, const Task t, float* scratch, const float (&acc)[6][Cfg<ND>::XPT]) {
+template <int ND> ION_HD void main_phase_store(int tid, const Geom& g, const Task t, float* scratch, bool accumulate, float (&acc)[6][Cfg<ND>::XPT]) {
     typedef Cfg<ND> C;
     constexpr int YZ = ND * ND;
+    if (tid >= C::TACC) return;
     const int yz = tid % YZ, xg = tid / YZ;
     const uint32_t y = (uint32_t)(yz % ND) * g.dsy + t.oy;
     const uint32_t z = ((uint32_t)(yz / ND) + (uint32_t)ND * t.wz) * g.dsz + t.oz;
@@ -373,6 +401,10 @@ template <int ND> ION_HD void main_phase_store(int tid, const Geom& g, const Tas
 #pragma unroll
     for (int c = 0; c < 6; c++) {
         float* p = row + (uint64_t)c * g.N;
+        if (accumulate) {  // a second source set adds to what the first pass left in the scratch field
+#pragma unroll
+            for (int i = 0; i < C::XPT; i++) acc[c][i] += p[i];
+        }
         if (C::XPT % 4 == 0) {
 #pragma unroll
             for (int i = 0; i < C::XPT; i += 4) *reinterpret_cast<float4*>(p + i) = make_float4(acc[c][i], acc[c][i + 1], acc[c][i + 2], acc[c][i + 3]);

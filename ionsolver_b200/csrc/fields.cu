@@ -711,6 +711,7 @@ __global__ void ION_EB_BOUNDS(BLOCK) k_update_e_b_pair(const __grid_constant__ K
         for (uint32_t fi = 0; fi < fs.n; fi++) {
             const ForeignDesc& fd = fs.d[fi];
             if (fabsf(fd.sx) > ION_FAR_SHIFT || fabsf(fd.sy) > ION_FAR_SHIFT || fabsf(fd.sz) > ION_FAR_SHIFT) continue;  // quirk Q18 domains
+            if (fd.fast == 2u) continue;  // already in E_dyn / B_dyn
             if (!fd.fast) {
                 foreign_generic(fd.flat0, fd.flat0 + fd.count);
                 continue;
@@ -878,7 +879,7 @@ __global__ void k_lod_gather(float* __restrict__ lods, uint32_t depth) {
 
 // ---- launchers used by api.cu ----
 // descriptors of the foreign domains in the order k_build_sources lays them out (ascending index, self skipped)
-static void describe_foreign(const KArgs& a, uint32_t nd, ForeignSet& fs) {
+static void describe_foreign(const KArgs& a, uint32_t nd, ForeignSet& fs, int skip_domain = -1) {
     fs.n = 0;
     const uint32_t dxy = a.dx * a.dy, dn = dxy * a.dz;
     if (dn <= 1u || dn - 1u > (uint32_t)MAX_FOREIGN) return;  // single domain, or too many: the kernel walks the flat table
@@ -901,20 +902,21 @@ static void describe_foreign(const KArgs& a, uint32_t nd, ForeignSet& fs) {
         f.sy = (float)((uint32_t)ddy * a.ny);
         f.sz = (float)((uint32_t)ddz * a.nz);
         f.fast = (level + 1u == a.lod_depth && 2u * ndf == nd && a.nx / ndf == 2u * (a.nx / nd) && a.ny >= ndf && a.nz >= ndf) ? 1u : 0u;
+        if ((int)d == skip_domain) f.fast = 2u;  // summed by the polyphase FFT pass (eb_fft.cu, second source set)
         entry += cnt;
         flat += cnt;
     }
 }
 
 template <int ND, int NC, int BLOCK, bool VOL>
-static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s, uint32_t mode = 0u) {
+static cudaError_t launch_pair(const KArgs& a, const LodSource* src, uint32_t own, uint32_t count, cudaStream_t s, uint32_t mode = 0u, int skip_domain = -1) {
     const size_t smem = (mode & 1u) ? 0 : (size_t)own * 2 * sizeof(float4);
     if (smem > 48u * 1024u) {
         cudaError_t e = cudaFuncSetAttribute(k_update_e_b_pair<ND, NC, BLOCK, VOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * fine_bytes(ND)));
         if (e != cudaSuccess) return e;
     }
     ForeignSet fs;
-    describe_foreign(a, ND, fs);
+    describe_foreign(a, ND, fs, skip_domain);
     const uint32_t threads_per_plane = (a.nx / ND) * (ND / NC) * a.ny;
     const dim3 grid((threads_per_plane + BLOCK - 1) / BLOCK, a.nz);
     k_update_e_b_pair<ND, NC, BLOCK, VOL><<<grid, BLOCK, smem, s>>>(a, src + own, count - own, fs, mode);
@@ -972,15 +974,22 @@ cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_
     return cudaGetLastError();
 }
 // Foreign-domain pyramids only (sim.cl:957-983), added to the E_dyn / B_dyn the polyphase FFT pass (eb_fft.cu) has written.
-cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches) {
+// `skip_domain`: a domain whose pyramid the FFT pass has summed already (-1 = none).
+cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, int skip_domain) {
     const uint32_t count = source_count(a.lod_depth, a.n_lod_own, a.dx, a.dy, a.dz, a.di);
     const uint32_t nd = 1u << a.lod_depth;
     const uint32_t own = nd * nd * nd;
     if (count <= own) return cudaSuccess;  // single domain
+    if (skip_domain >= 0) {  // anything left?  (slabs above are skipped by the fast path: quirk Q18)
+        bool any = false;
+        for (uint32_t d = 0; d < a.di && !any; d++) any = (int)d != skip_domain;
+        if (!any) return cudaSuccess;
+    }
     LodSource* src = reinterpret_cast<LodSource*>(scratch_sources);
     k_build_sources<<<(count + 255u) / 256u, 256, 0, s>>>(a, src, count);
     *launches += 2;
-    return a.lod_depth == 4u ? launch_pair<16, 16, 256, true>(a, src, own, count, s, 3u) : launch_pair<8, 8, 256, false>(a, src, own, count, s, 3u);
+    return a.lod_depth == 4u ? launch_pair<16, 16, 256, true>(a, src, own, count, s, 3u, skip_domain)
+                             : launch_pair<8, 8, 256, false>(a, src, own, count, s, 3u, skip_domain);
 }
 size_t lod_source_bytes(uint32_t lod_depth, uint32_t n_lod_own, uint32_t dx, uint32_t dy, uint32_t dz, uint32_t di) {
     return (size_t)source_count(lod_depth, n_lod_own, dx, dy, dz, di) * sizeof(LodSource);

@@ -22,9 +22,22 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     g.dsx = nx / ND; g.dsy = ny / ND; g.dsz = nz / ND;
     g.n_lod_own = n_lod_own; g.lo = n_lod_own - ND * ND * ND; g.cz0 = g.lo / (ND * ND);
     g.dx = 1; g.dy = 1; g.dz = dz; g.ke = 1.5f; g.kmu = 0.25f;
+    constexpr int NF = ND / 2;
+    // second source set: the level D-1 pyramid of the slab below (only when this slab has one: dz > 1 and block sizes commensurate)
+    const bool foreign = dz > 1 && nx / NF == 2 * g.dsx && ny / NF == 2 * g.dsy && nz / NF == 2 * g.dsz;
+    SourceSet sets[2];
+    sets[0] = SourceSet{0u, 0u, -(int32_t)g.cz0, -0.5f * g.dsx, -0.5f * g.dsy, -0.5f * g.dsz};
+    sets[1] = SourceSet{1u, n_lod_own, (int32_t)(nz / g.dsz), 0.0f, 0.0f, (float)(nz % g.dsz)};
+    const int nsets = foreign ? 2 : 1;
     std::mt19937 rng(1234);
     std::uniform_real_distribution<float> U(-1.f, 1.f);
-    std::vector<float> lod(4 * (size_t)n_lod_own);
+    std::vector<float> lod(4 * ((size_t)n_lod_own + NF * NF * NF));
+    for (uint32_t d = n_lod_own; d < n_lod_own + NF * NF * NF; d++) {
+        lod[4 * d] = 60.0f * (1.0f + 0.2f * U(rng));
+        lod[4 * d + 1] = 0.1f + 0.02f * U(rng);
+        lod[4 * d + 2] = 0.01f + 0.02f * U(rng);
+        lod[4 * d + 3] = 0.02f * U(rng);
+    }
     for (uint32_t d = 0; d < n_lod_own; d++) {
         const bool filled = dz > 1 ? true : d < (uint32_t)(ND * ND * ND);  // single domain: nothing fills the tail (quirk Q5)
         lod[4 * d] = filled ? 8.0f * (1.0f + 0.2f * U(rng)) : 0.0f;
@@ -44,19 +57,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     const int ntasks = (int)tasks.size();
     std::vector<float2> khat(C::khat_per_task * ntasks), shat(C::shat_count);
     std::vector<float2> S(C::H * C::M * C::ROW);
-    for (int t = 0; t < ntasks; t++)
-        for (int c = 0; c < 3; c++) {
-            for (int tid = 0; tid < C::T; tid++) khat_phase_x<ND>(tid, C::T, g, tasks[t], c, S.data());
-            for (int tid = 0; tid < C::T; tid++) khat_phase_y<ND>(tid, C::T, S.data());
-            for (int tid = 0; tid < C::T; tid++) khat_phase_z<ND>(tid, C::T, t, c, S.data(), khat.data());
-        }
     std::vector<float2> plane(C::M * C::ROW);
-    for (int j = 0; j < 4; j++)
-        for (int kx = 0; kx < C::H; kx++) {
-            for (int tid = 0; tid < 128; tid++) src_phase_x<ND>(tid, 128, g, lod.data(), kx, j, plane.data());
-            for (int tid = 0; tid < 128; tid++) src_phase_y<ND>(tid, 128, plane.data());
-            for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), shat.data());
-        }
     std::vector<uint8_t> flags(g.N, 0);
     std::vector<float> Es(3 * g.N), Bs(3 * g.N), Ed(3 * g.N, -7.f), Bd(3 * g.N, -7.f);
     for (auto& v : Es) v = U(rng);
@@ -64,22 +65,37 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     flags[5 + 7 * nx + 9 * nx * ny] = 0x01;  // one solid cell: must stay untouched
     std::vector<float2> W((size_t)C::P * C::PLANE), tw(C::M);
     std::vector<float> scratch((size_t)6 * g.N, 0.0f);
+    std::vector<float2> S0((size_t)C::P * C::SLOT);
     for (int i = 0; i < C::M; i++) tw[i] = make_float2(tw_cos32(i * (32 / C::M)), tw_sin32(i * (32 / C::M)));
     std::vector<float> accreg((size_t)C::T * 6 * C::XPT);
+    for (int set = 0; set < nsets; set++) {
+    for (int t = 0; t < ntasks; t++)
+        for (int c = 0; c < 3; c++) {
+            for (int tid = 0; tid < C::T; tid++) khat_phase_x<ND>(tid, C::T, g, sets[set], tasks[t], c, S.data());
+            for (int tid = 0; tid < C::T; tid++) khat_phase_y<ND>(tid, C::T, S.data());
+            for (int tid = 0; tid < C::T; tid++) khat_phase_z<ND>(tid, C::T, t, c, S.data(), khat.data());
+        }
+    for (int j = 0; j < 4; j++)
+        for (int kx = 0; kx < C::H; kx++) {
+            for (int tid = 0; tid < 128; tid++) src_phase_x<ND>(tid, 128, g, sets[set], lod.data(), kx, j, plane.data());
+            for (int tid = 0; tid < 128; tid++) src_phase_y<ND>(tid, 128, plane.data());
+            for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), shat.data());
+        }
     for (int t = 0; t < ntasks; t++) {
         const float2* kt = khat.data() + C::khat_per_task * t;
         std::fill(accreg.begin(), accreg.end(), 0.0f);
         for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
             const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
-            main_stage_host<ND>(kt, shat.data(), kx0, np, W.data());
-            for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, shat.data(), kx0, np, W.data());
+            main_stage_host<ND>(kt, shat.data(), kx0, np, W.data(), S0.data());
+            for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, S0.data(), np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_z<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_y<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++)
                 main_phase_accumulate<ND>(tid, kx0, np, W.data(), tw.data(), *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
         }
         for (int tid = 0; tid < C::T; tid++)
-            main_phase_store<ND>(tid, g, tasks[t], scratch.data(), *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
+            main_phase_store<ND>(tid, g, tasks[t], scratch.data(), set > 0, *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
+    }
     }
     {  // k_eb_combine: one block per row
         std::vector<float> tile((size_t)(nx / ND) * (ND + 1) + ND + 1);
@@ -120,6 +136,18 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
                     e[0] += q * px; e[1] += q * py; e[2] += q * pz;
                     b[0] += q * (vy * pz - vz * py); b[1] += q * (vz * px - vx * pz); b[2] += q * (vx * py - vy * px);
                 }
+                if (foreign)  // sim.cl:957-983: level D-1 of the slab below, centres shifted by the halo-inclusive slab height (quirk Q8)
+                    for (uint32_t f = 0; f < (uint32_t)(NF * NF * NF); f++) {
+                        const uint32_t d = n_lod_own + f;
+                        const double bsx = nx / NF, bsy = ny / NF, bsz = nz / NF;
+                        const double cx = (f % NF) * bsx + 0.5 * bsx, cy = ((f / NF) % NF) * bsy + 0.5 * bsy, cz = (f / (NF * NF)) * bsz + 0.5 * bsz - (double)nz;
+                        const double rx = x - cx, ry = y - cy, rz = z - cz;
+                        const double r2 = rx * rx + ry * ry + rz * rz, inv = 1.0 / (r2 * std::sqrt(r2));
+                        const double q = lod[4 * d], vx = lod[4 * d + 1], vy = lod[4 * d + 2], vz = lod[4 * d + 3];
+                        const double px = rx * inv, py = ry * inv, pz = rz * inv;
+                        e[0] += q * px; e[1] += q * py; e[2] += q * pz;
+                        b[0] += q * (vy * pz - vz * py); b[1] += q * (vz * px - vx * pz); b[2] += q * (vx * py - vy * px);
+                    }
                 for (int c = 0; c < 3; c++) {
                     const double re = Es[c * g.N + n] + (double)g.ke * e[c], rb = Bs[c * g.N + n] + (double)g.kmu * b[c];
                     const double de = Ed[c * g.N + n] - re, db = Bd[c * g.N + n] - rb;
@@ -129,7 +157,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
                 checked++;
             }
     const double le = std::sqrt(num[0] / den[0]), lb = std::sqrt(num[1] / den[1]);
-    printf("{\"nd\": %d, \"tasks\": %d, \"cells\": %ld, \"rel_l2_E\": %.3e, \"rel_l2_B\": %.3e, \"max_abs_err\": %.3e, \"untouched_bad\": %ld}\n", ND, ntasks,
+    printf("{\"nd\": %d, \"source_sets\": %d, \"tasks\": %d, \"cells\": %ld, \"rel_l2_E\": %.3e, \"rel_l2_B\": %.3e, \"max_abs_err\": %.3e, \"untouched_bad\": %ld}\n", ND, nsets, ntasks,
            checked, le, lb, maxerr, untouched_bad);
     return (le < 1e-5 && lb < 1e-5 && untouched_bad == 0) ? 0 : 1;
 }
