@@ -24,7 +24,7 @@ struct EbFftPlan {
     int foreign_domain;  // domain index whose pyramid is set 1, -1 = none (the direct kernel must then sum it)
     Task* tasks;
     float2* khat;   // nsets * ntasks * khat_per_task
-    float2* shat;
+    float2* shat;   // nsets * shat_count
     float* scratch;  // the sums of a step before they are combined with the static fields: 6 floats per cell, rows permuted
     size_t khat_bytes;
 };
@@ -85,10 +85,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // One block per task.  The K^ slots of the next group of kx planes stream into the idle half of the work buffer (bulk copies
 // armed on an mbarrier by one thread) while the block transforms the current group: the HBM latency of the only large operand
 // is hidden behind the FFT phases, and the products are formed in place where the copy landed.
-template <int ND>
+// NSETS = 2 (a slab with a lower neighbour): K^ of the neighbour's level D-1 pyramid is staged into the B slots instead of
+// s^_1..3, both source spectra are read from L2 in the product phase, and the two convolutions share every inverse transform.
+template <int ND, int NSETS>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
-             float* __restrict__ scratch, const int accumulate) {
+             const float2* __restrict__ khat2, const float2* __restrict__ shat2, float* __restrict__ scratch, const int accumulate) {
     typedef Cfg<ND> C;
     extern __shared__ __align__(128) unsigned char eb_smem[];
     __shared__ __align__(8) uint64_t bars[2];
@@ -99,6 +101,7 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
     const Task t = tasks[blockIdx.x];
     const float2* kt = khat + (size_t)blockIdx.x * C::khat_per_task;
+    const float2* kt2 = NSETS == 2 ? khat2 + (size_t)blockIdx.x * C::khat_per_task : nullptr;
     if (tid == 0) {
         mbar_init(&bars[0], 1u);
         mbar_init(&bars[1], 1u);
@@ -111,15 +114,15 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
         uint64_t* bar = &bars[it & 1];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the targets were last touched by ordinary loads / stores
-        mbar_expect_tx(bar, (uint32_t)(np * 7 * C::SLOT * sizeof(float2)));
+        mbar_expect_tx(bar, (uint32_t)(np * (NSETS == 2 ? 6 : 7) * C::SLOT * sizeof(float2)));
         for (int p = 0; p < np; p++) {
-            bulk_g2s(S0 + (size_t)p * C::SLOT, shat + ((size_t)kx0 + p) * C::SLOT, (uint32_t)(C::SLOT * sizeof(float2)), bar);
+            if (NSETS == 1) bulk_g2s(S0 + (size_t)p * C::SLOT, shat + ((size_t)kx0 + p) * C::SLOT, (uint32_t)(C::SLOT * sizeof(float2)), bar);
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)c * C::SLOT, kt + ((size_t)c * C::H + kx0 + p) * C::SLOT,
                          (uint32_t)(C::SLOT * sizeof(float2)), bar);
-                bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT, shat + ((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT,
-                         (uint32_t)(C::SLOT * sizeof(float2)), bar);
+                const float2* second = NSETS == 2 ? kt2 + ((size_t)c * C::H + kx0 + p) * C::SLOT : shat + ((size_t)(1 + c) * C::H + kx0 + p) * C::SLOT;
+                bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT, second, (uint32_t)(C::SLOT * sizeof(float2)), bar);
             }
         }
     };
@@ -133,7 +136,8 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
         mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-        main_phase_product<ND>(tid, S0, np, Wb);
+        if (NSETS == 2) main_phase_product2<ND>(tid, shat, shat2, kx0, np, Wb);
+        else main_phase_product<ND>(tid, S0, np, Wb);
         __syncthreads();
         // Every thread is past the x accumulation of iteration it - 1 (which read the other buffer) and past this iteration's
         // products (which read S0): both are free, the operands of iteration it + 1 can land while this one is transformed.
@@ -277,8 +281,6 @@ void eb_fft_destroy(EbFftPlan* p) {
 template <int ND> static cudaError_t build_khat(EbFftPlan* p, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
-    if (e != cudaSuccess) return e;
     for (int set = 0; set < p->nsets; set++)
         k_eb_khat<ND><<<dim3(p->ntasks, 3), 256, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task);
     return cudaGetLastError();
@@ -334,7 +336,7 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->khat, p->khat_bytes);
-    if (e == cudaSuccess) e = cudaMalloc((void**)&p->shat, sh * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->shat, (size_t)p->nsets * sh * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->scratch, scratch_bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `tasks` is a local vector
@@ -351,13 +353,16 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
 
 template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& a, cudaStream_t s) {
     // function attributes are per device: set on every launch (a host-side table lookup)
-    cudaError_t e = cudaFuncSetAttribute(k_eb_fft<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
+    cudaError_t e = p->nsets == 2 ? cudaFuncSetAttribute(k_eb_fft<ND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem)
+                                  : cudaFuncSetAttribute(k_eb_fft<ND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
     if (e != cudaSuccess) return e;
-    for (int set = 0; set < p->nsets; set++) {  // the source spectrum buffer is reused: the launches are ordered on the stream
-        k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat);
-        k_eb_fft<ND><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task, p->shat,
-                                                                        p->scratch, set);
-    }
+    const size_t kstride = (size_t)p->ntasks * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
+    for (int set = 0; set < p->nsets; set++)
+        k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride);
+    if (p->nsets == 2)
+        k_eb_fft<ND, 2><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->khat + kstride, p->shat + sstride, p->scratch, 0);
+    else
+        k_eb_fft<ND, 1><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
     const uint32_t tile_len = (a.nx / ND) * (ND + 1) + ND + 1;
     const size_t csmem = (size_t)6 * tile_len * sizeof(float);
     const uint32_t threads = a.nx < 256u ? ((a.nx + 31u) / 32u) * 32u : 256u;
@@ -380,7 +385,7 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    *launches += 1u + 2u * (uint64_t)p->nsets;
+    *launches += 2u + (uint64_t)p->nsets;
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }

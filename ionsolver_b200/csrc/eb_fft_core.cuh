@@ -117,6 +117,25 @@ ION_HD constexpr int ilog2(int m) { return m <= 1 ? 0 : 1 + ilog2(m >> 1); }
 // In-register radix-2 decimation-in-time FFT of M = 16 or 32 complex points.  INV = false: e^{-2 pi i k n / M};
 // INV = true: e^{+...}, unnormalised.  Everything is unrolled, so all indices and twiddles are compile-time constants;
 // outputs the caller never reads (pruned transforms) and inputs that are literal zeros fold away.
+// complex add / subtract as ONE packed FP32 instruction on the device (add.f32x2 / fma.f32x2 with -1): each lane is an IEEE
+// operation, so the results equal the scalar form bit for bit; the butterflies' add/sub are 70 % of an FFT's instructions
+#ifndef ION_FFT_PACKED
+#define ION_FFT_PACKED 1
+#endif
+ION_HD float2 cadd(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && ION_FFT_PACKED
+    return __fadd2_rn(a, b);
+#else
+    return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+ION_HD float2 csub(float2 a, float2 b) {
+#if defined(__CUDA_ARCH__) && ION_FFT_PACKED
+    return __ffma2_rn(b, make_float2(-1.0f, -1.0f), a);
+#else
+    return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
 template <int M, int LEN, bool INV> struct FftStage {  // butterflies of span LEN, after all shorter spans
     static ION_HD void run(float2 (&a)[M]) {
         FftStage<M, LEN / 2, INV>::run(a);
@@ -136,8 +155,8 @@ template <int M, int LEN, bool INV> struct FftStage {  // butterflies of span LE
                     const float c = tw_cos32(ti), sn = INV ? tw_sin32(ti) : -tw_sin32(ti);
                     w = make_float2(fmaf(v.x, c, -(v.y * sn)), fmaf(v.x, sn, v.y * c));
                 }
-                a[i + k] = make_float2(u.x + w.x, u.y + w.y);
-                a[i + k + half] = make_float2(u.x - w.x, u.y - w.y);
+                a[i + k] = cadd(u, w);
+                a[i + k + half] = csub(u, w);
             }
         }
     }
@@ -334,6 +353,48 @@ template <int ND> ION_HD void main_phase_product(int tid, const float2* S0, int 
         w[4 * C::SLOT] = cmul_sub(s3, k0, s1, k2);
         w[5 * C::SLOT] = cmul_sub(s1, k1, s2, k0);
     }
+}
+// phase 1 with TWO source sets (a slab with a lower neighbour): K^ of the own level was staged in the E slots, K^' of the
+// neighbour's level D-1 in the B slots; both source spectra come from L2.  The spectra of the two convolutions are ADDED here,
+// so that one inverse transform serves both (the transform is linear) -- the second set costs products, not FFTs.
+template <int ND> ION_HD void main_phase_product2(int tid, const float2* shat, const float2* shat2, int kx0, int np, float2* W) {
+    typedef Cfg<ND> C;
+    constexpr int MM = C::M * C::M;
+    constexpr size_t CS = (size_t)C::H * C::SLOT;  // component stride of s^
+#pragma unroll 2
+    for (int idx = tid; idx < np * MM; idx += C::T) {
+        const int p = idx / MM, f = idx % MM;
+        const int kz = f / C::M, ky = f % C::M;
+        const int o = kz * C::ROW + ky;
+        const size_t gi = (size_t)(kx0 + p) * C::SLOT + o;
+        float2* w = W + (size_t)p * C::PLANE + o;
+        const float2 s0 = ION_LDG2(shat + gi), s1 = ION_LDG2(shat + CS + gi), s2 = ION_LDG2(shat + 2 * CS + gi), s3 = ION_LDG2(shat + 3 * CS + gi);
+        const float2 t0 = ION_LDG2(shat2 + gi), t1 = ION_LDG2(shat2 + CS + gi), t2 = ION_LDG2(shat2 + 2 * CS + gi), t3 = ION_LDG2(shat2 + 3 * CS + gi);
+        const float2 k0 = w[0], k1 = w[C::SLOT], k2 = w[2 * C::SLOT];
+        const float2 l0 = w[3 * C::SLOT], l1 = w[4 * C::SLOT], l2 = w[5 * C::SLOT];
+        float2 E[3], B[3];
+        E[0] = cmul(k0, s0); E[1] = cmul(k1, s0); E[2] = cmul(k2, s0);
+        B[0] = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
+        B[1] = cmul_sub(s3, k0, s1, k2);
+        B[2] = cmul_sub(s1, k1, s2, k0);
+        const float2 e0 = cmul(l0, t0), e1 = cmul(l1, t0), e2 = cmul(l2, t0);
+        const float2 b0 = cmul_sub(t2, l2, t3, l1), b1 = cmul_sub(t3, l0, t1, l2), b2 = cmul_sub(t1, l1, t2, l0);
+        w[0] = make_float2(E[0].x + e0.x, E[0].y + e0.y);
+        w[C::SLOT] = make_float2(E[1].x + e1.x, E[1].y + e1.y);
+        w[2 * C::SLOT] = make_float2(E[2].x + e2.x, E[2].y + e2.y);
+        w[3 * C::SLOT] = make_float2(B[0].x + b0.x, B[0].y + b0.y);
+        w[4 * C::SLOT] = make_float2(B[1].x + b1.x, B[1].y + b1.y);
+        w[5 * C::SLOT] = make_float2(B[2].x + b2.x, B[2].y + b2.y);
+    }
+}
+template <int ND> inline void main_stage2_host(const float2* khat_task, const float2* khat2_task, int kx0, int np, float2* W) {
+    typedef Cfg<ND> C;
+    for (int p = 0; p < np; p++)
+        for (int c = 0; c < 3; c++)
+            for (int i = 0; i < C::SLOT; i++) {
+                W[(size_t)p * C::PLANE + (size_t)c * C::SLOT + i] = khat_task[((size_t)c * C::H + kx0 + p) * C::SLOT + i];
+                W[(size_t)p * C::PLANE + (size_t)(3 + c) * C::SLOT + i] = khat2_task[((size_t)c * C::H + kx0 + p) * C::SLOT + i];
+            }
 }
 // phase 2: inverse FFT along kz of every column (p, spectrum, ky); only the ND outputs z that exist are kept (in place)
 template <int ND> ION_HD void main_phase_z(int tid, int np, float2* W) {

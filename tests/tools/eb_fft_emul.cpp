@@ -68,34 +68,42 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     std::vector<float2> S0((size_t)C::P * C::SLOT);
     for (int i = 0; i < C::M; i++) tw[i] = make_float2(tw_cos32(i * (32 / C::M)), tw_sin32(i * (32 / C::M)));
     std::vector<float> accreg((size_t)C::T * 6 * C::XPT);
+    std::vector<float2> khat2(nsets == 2 ? C::khat_per_task * ntasks : 0), shat2(nsets == 2 ? C::shat_count : 0);
     for (int set = 0; set < nsets; set++) {
-    for (int t = 0; t < ntasks; t++)
-        for (int c = 0; c < 3; c++) {
-            for (int tid = 0; tid < C::T; tid++) khat_phase_x<ND>(tid, C::T, g, sets[set], tasks[t], c, S.data());
-            for (int tid = 0; tid < C::T; tid++) khat_phase_y<ND>(tid, C::T, S.data());
-            for (int tid = 0; tid < C::T; tid++) khat_phase_z<ND>(tid, C::T, t, c, S.data(), khat.data());
-        }
-    for (int j = 0; j < 4; j++)
-        for (int kx = 0; kx < C::H; kx++) {
-            for (int tid = 0; tid < 128; tid++) src_phase_x<ND>(tid, 128, g, sets[set], lod.data(), kx, j, plane.data());
-            for (int tid = 0; tid < 128; tid++) src_phase_y<ND>(tid, 128, plane.data());
-            for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), shat.data());
-        }
-    for (int t = 0; t < ntasks; t++) {
+        float2* kh = set == 0 ? khat.data() : khat2.data();
+        float2* sh = set == 0 ? shat.data() : shat2.data();
+        for (int t = 0; t < ntasks; t++)
+            for (int c = 0; c < 3; c++) {
+                for (int tid = 0; tid < C::T; tid++) khat_phase_x<ND>(tid, C::T, g, sets[set], tasks[t], c, S.data());
+                for (int tid = 0; tid < C::T; tid++) khat_phase_y<ND>(tid, C::T, S.data());
+                for (int tid = 0; tid < C::T; tid++) khat_phase_z<ND>(tid, C::T, t, c, S.data(), kh);
+            }
+        for (int j = 0; j < 4; j++)
+            for (int kx = 0; kx < C::H; kx++) {
+                for (int tid = 0; tid < 128; tid++) src_phase_x<ND>(tid, 128, g, sets[set], lod.data(), kx, j, plane.data());
+                for (int tid = 0; tid < 128; tid++) src_phase_y<ND>(tid, 128, plane.data());
+                for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), sh);
+            }
+    }
+    for (int t = 0; t < ntasks; t++) {  // one pass: with two source sets their spectra are added before the inverse transform
         const float2* kt = khat.data() + C::khat_per_task * t;
         std::fill(accreg.begin(), accreg.end(), 0.0f);
         for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
             const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
-            main_stage_host<ND>(kt, shat.data(), kx0, np, W.data(), S0.data());
-            for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, S0.data(), np, W.data());
+            if (nsets == 2) {
+                main_stage2_host<ND>(kt, khat2.data() + C::khat_per_task * t, kx0, np, W.data());
+                for (int tid = 0; tid < C::T; tid++) main_phase_product2<ND>(tid, shat.data(), shat2.data(), kx0, np, W.data());
+            } else {
+                main_stage_host<ND>(kt, shat.data(), kx0, np, W.data(), S0.data());
+                for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, S0.data(), np, W.data());
+            }
             for (int tid = 0; tid < C::T; tid++) main_phase_z<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_y<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++)
                 main_phase_accumulate<ND>(tid, kx0, np, W.data(), tw.data(), *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
         }
         for (int tid = 0; tid < C::T; tid++)
-            main_phase_store<ND>(tid, g, tasks[t], scratch.data(), set > 0, *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
-    }
+            main_phase_store<ND>(tid, g, tasks[t], scratch.data(), false, *reinterpret_cast<float(*)[6][C::XPT]>(&accreg[(size_t)tid * 6 * C::XPT]));
     }
     {  // k_eb_combine: one block per row
         std::vector<float> tile((size_t)(nx / ND) * (ND + 1) + ND + 1);
