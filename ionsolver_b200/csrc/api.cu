@@ -39,7 +39,7 @@ cudaError_t launch_voxelize(const KArgs& a, uint32_t direction, uint8_t flag, co
 size_t compaction_scratch_bytes(uint64_t N);
 cudaError_t count_sources(const KArgs& a, uint8_t mask, uint32_t* counts, uint32_t* host_total, cudaStream_t s);
 size_t field_source_bytes(uint32_t count);
-cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s);
+cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s, int fast);
 cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void* table, cudaStream_t s);
 
 // FP32 issue-peak probe for bench.py's compute roofline (MEASURED_PEAKS.json only carries HBM and BF16 numbers):
@@ -655,7 +655,7 @@ static int precompute(ion_domain_t* d, int which) {
     void* table = nullptr;
     ION_CUDA(cudaMallocAsync(&table, field_source_bytes(total), d->stream));
     if (which == 0) {
-        e = launch_precompute_b(d->k, d->cp_counts, table, d->stream);
+        e = launch_precompute_b(d->k, d->cp_counts, table, d->stream, d->precompute_fast ? 1 : 0);
         g_launches += 5;
     } else {
         float* E = which == 1 ? d->k.E_stat : (float*)d->buf[ION_FIELD_E_VAR];
@@ -670,6 +670,13 @@ static int precompute(ion_domain_t* d, int which) {
 int ion_enqueue_precompute_b(ion_domain_t* d) { return precompute(d, 0); }
 int ion_enqueue_precompute_e(ion_domain_t* d) { return precompute(d, 1); }
 int ion_enqueue_precompute_e_ecr(ion_domain_t* d) { return precompute(d, 2); }
+
+int ion_domain_set_precompute_mode(ion_domain_t* d, int mode) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (mode < 0 || mode > 1) return fail(ION_ERR_INVALID, "precompute mode %d (0 = reference arithmetic and order, 1 = fast)", mode);
+    d->precompute_fast = mode == 1;
+    return ION_OK;
+}
 
 int ion_domain_set_ecr_freq(ion_domain_t* d, float ecrf) {
     if (!d) return fail(ION_ERR_INVALID, "NULL domain");

@@ -240,6 +240,55 @@ __global__ void __launch_bounds__(SF_BLOCK) k_psi(const __grid_constant__ KArgs 
     if (n < total) psi[n] = (float)((double)psic / (4.0 * 3.14159265358979323846));  // `4.0f * M_PI` is a double product, sim.cl:1250
 }
 
+// Fast mode of psi_from_mesh (opt-in, ion_domain_set_precompute_mode): the same compacted-source sum, organised for FP32 issue
+// instead of for bit-identity -- four consecutive outputs of a row per thread (dy, dz, dy^2 + dz^2 and the y/z part of M.r are shared
+// by the four), r^-3 from one rsqrt instead of sqrt + cube + IEEE division, fused multiply-adds, packed FP32 for the two output
+// pairs.  ~9 instructions per (output, source) pair instead of ~35.  Differs from the exact mode by rounding only (relative L2
+// ~1e-6 in psi; tests/test_gpu_parity.py::test_fast_precompute_mode).
+constexpr int PSI_OUT = 4;
+__global__ void __launch_bounds__(SF_BLOCK) k_psi_fast(const __grid_constant__ KArgs a, float* __restrict__ psi, const FieldSource* __restrict__ src,
+                                                        const uint32_t* __restrict__ count_p) {
+    __shared__ float4 s_a[SF_CHUNK], s_b[SF_CHUNK];
+    const uint32_t count = *count_p;
+    const uint32_t lx = a.nx + 2u, ly = a.ny + 2u, lz = a.nz + 2u;
+    const uint32_t x0 = (blockIdx.x * SF_BLOCK + threadIdx.x) * PSI_OUT, y = blockIdx.y, z = blockIdx.z;
+    const float cy = (float)y, cz = (float)z;
+    const float2 cxa = make_float2((float)x0, (float)(x0 + 1u)), cxb = make_float2((float)(x0 + 2u), (float)(x0 + 3u));
+    float2 pa = make_float2(0.f, 0.f), pb = make_float2(0.f, 0.f);
+    for (uint32_t base = 0; base < count; base += SF_CHUNK) {
+        const uint32_t m = min((uint32_t)SF_CHUNK, count - base);
+        __syncthreads();
+        for (uint32_t k = threadIdx.x; k < m; k += SF_BLOCK) {
+            const float4* p = reinterpret_cast<const float4*>(src + base + k);
+            s_a[k] = p[0];
+            s_b[k] = p[1];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (uint32_t k = 0; k < m; k++) {
+            const float4 c = s_a[k], mg = s_b[k];
+            const float dy = cy - c.y, dz = cz - c.z;
+            const float dyz2 = fmaf(dy, dy, dz * dz), myz = fmaf(dy, mg.y, dz * mg.z);
+            const float2 ncx = make_float2(-c.x, -c.x), d2 = make_float2(dyz2, dyz2), m2 = make_float2(myz, myz), mx2 = make_float2(mg.x, mg.x);
+            const float2 dxa = __fadd2_rn(cxa, ncx), dxb = __fadd2_rn(cxb, ncx);
+            const float2 ra = __ffma2_rn(dxa, dxa, d2), rb = __ffma2_rn(dxb, dxb, d2);
+            // r = 0 only for the output that sits on the source cell itself: the reference skips it (sim.cl:1245)
+            const float2 ia = make_float2(ra.x > 0.f ? rsqrtf(ra.x) : 0.f, ra.y > 0.f ? rsqrtf(ra.y) : 0.f);
+            const float2 ib = make_float2(rb.x > 0.f ? rsqrtf(rb.x) : 0.f, rb.y > 0.f ? rsqrtf(rb.y) : 0.f);
+            const float2 i3a = __fmul2_rn(__fmul2_rn(ia, ia), ia), i3b = __fmul2_rn(__fmul2_rn(ib, ib), ib);
+            pa = __ffma2_rn(__ffma2_rn(dxa, mx2, m2), i3a, pa);
+            pb = __ffma2_rn(__ffma2_rn(dxb, mx2, m2), i3b, pb);
+        }
+    }
+    if (y >= ly || z >= lz) return;
+    const uint64_t row = ((uint64_t)y + (uint64_t)z * ly) * lx;
+    const float inv4pi = 0.07957747154594767f;
+    const float out[4] = {pa.x * inv4pi, pa.y * inv4pi, pb.x * inv4pi, pb.y * inv4pi};
+#pragma unroll
+    for (int i = 0; i < PSI_OUT; i++)
+        if (x0 + (uint32_t)i < lx) psi[row + x0 + (uint32_t)i] = out[i];
+}
+
 // static_b_from_mesh, sim.cl:1265-1276
 __global__ void k_static_b(const __grid_constant__ KArgs a, const float* __restrict__ psi) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
@@ -336,13 +385,18 @@ cudaError_t count_sources(const KArgs& a, uint8_t mask, uint32_t* counts, uint32
 }
 size_t field_source_bytes(uint32_t count) { return (size_t)(count ? count : 1u) * sizeof(FieldSource); }
 
-cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s) {
+cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s, int fast) {
     FieldSource* src = reinterpret_cast<FieldSource*>(table);
     cudaError_t e = compact(a, ION_TYPE_M, counts, src, a.B_dyn, 1, 1.0f, s);  // sim.cl:1240-1244 (coordinates(i)+1)
     if (e != cudaSuccess) return e;
     const uint32_t nblocks = (uint32_t)((a.N + CP_BLOCK - 1) / CP_BLOCK);
     const uint64_t total = (uint64_t)(a.nx + 2u) * (a.ny + 2u) * (a.nz + 2u);
-    k_psi<<<(unsigned)((total + SF_BLOCK - 1) / SF_BLOCK), SF_BLOCK, 0, s>>>(a, a.E_dyn, src, counts + nblocks);
+    if (fast) {
+        const uint32_t per_block = SF_BLOCK * PSI_OUT;
+        k_psi_fast<<<dim3((a.nx + 2u + per_block - 1u) / per_block, a.ny + 2u, a.nz + 2u), SF_BLOCK, 0, s>>>(a, a.E_dyn, src, counts + nblocks);
+    } else {
+        k_psi<<<(unsigned)((total + SF_BLOCK - 1) / SF_BLOCK), SF_BLOCK, 0, s>>>(a, a.E_dyn, src, counts + nblocks);
+    }
     unsigned b = ((a.nx + 31u) / 32u) * 32u;
     if (b > 128u) b = 128u;
     k_static_b<<<dim3((a.nx + b - 1u) / b, a.ny, a.nz), b, 0, s>>>(a, a.E_dyn);

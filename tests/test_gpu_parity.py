@@ -411,6 +411,33 @@ def test_ion_file_round_trip(gpu_lib, tmp_path):
         x.close()
 
 
+def test_fast_precompute_mode(golden, gpu_lib):
+    """ion_domain_set_precompute_mode(1): psi_from_mesh as an rsqrt / FMA sum with four outputs per thread.  Same sources, same sum,
+    different rounding: psi within 1e-5 relative L2 of the exact mode (which is bit-identical to the reference build, previous
+    test), B_stat -- central differences of psi -- within 1e-4."""
+    from ionsolver_b200 import lbm as L
+    g = golden["voxelize"]
+    out = {}
+    for mode in (0, 1):
+        cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=48, n_y=40, n_z=44, nu=0.05, ext_volume_force=True,
+                           ext_magneto_hydro=True, mhd_lod_depth=2)
+        cfg.units.set(48.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 1e-10, 1.0)
+        gpu = product(cfg)
+        kind = {"Solid": L.ModelType.Solid, "Magnet": L.ModelType.Magnet, "Charged": L.ModelType.Charged, "ChargedECR": L.ModelType.ChargedECR}
+        for i, (f, k, val, origin) in enumerate(g["config"]["meshes"]):
+            gpu.import_mesh(os.path.join(cases.STL_DIR, f), 1.0, origin[0], origin[1], origin[2], 0.0, 0.0, 0.0)
+            gpu.voxelise_mesh(i, kind[k], val)
+        for d in gpu.domains:
+            d.set_precompute_mode(mode)
+        gpu.precompute_B()
+        d = gpu.domains[0]
+        out[mode] = (d.read(cases.FIELD_OF["e_dyn"])[: (cfg.n_x + 2) * (cfg.n_y + 2) * (cfg.n_z + 2)].copy(), d.read(cases.FIELD_OF["b_stat"]).copy())
+        gpu.close()
+    assert sha(out[0][0]) == g["psi"]["sha256"]  # the exact mode is the reference's result
+    assert rel_l2(out[1][0], out[0][0]) < 1e-5 and rel_l2(out[1][1], out[0][1]) < 1e-4, (rel_l2(out[1][0], out[0][0]), rel_l2(out[1][1], out[0][1]))
+    assert not same_bits(out[1][0], out[0][0])  # the fast kernel really ran
+
+
 def test_reference_stl_assets_through_the_cuda_voxeliser(golden, gpu_lib):
     """The reference's own STL files (stl/*.stl, copied to tests/golden/stl/ref as fixtures) through the CUDA voxeliser and
     static-field kernels, against SHA-256 of what the reference's kernels produce (tests/golden/make_golden.py::ref_stl_vectors):
