@@ -22,6 +22,7 @@ template <int VS> cudaError_t launch_initialize_vs(const KArgs& a, int fp, bool 
 cudaError_t launch_update_e_b(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, bool exact);
 cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cudaStream_t s, uint64_t* launches, int skip_domain);
 int eb_fft_plan_foreign_domain(const EbFftPlan* p);
+bool eb_fft_plan_far_handled(const EbFftPlan* p);
 cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, EbFftPlan** out, uint64_t* launches);
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches);
 void eb_fft_destroy(EbFftPlan* p);
@@ -566,7 +567,10 @@ int ion_enqueue_update_e_b_dyn(ion_domain_t* d) {
     }
     if (d->eb_plan && !d->deterministic) {
         e = eb_fft_launch(d->eb_plan, d->k, d->stream, &l);
-        if (e == cudaSuccess) e = launch_update_e_b_foreign(d->k, d->lod_sources, d->stream, &l, eb_fft_plan_foreign_domain(d->eb_plan));
+        // what the FFT pass did not sum: every foreign pyramid when the geometry kept the neighbour off the FFT path, else the far
+        // slabs -- unless those went through the Taylor tensors of k_eb_combine
+        if (e == cudaSuccess && !eb_fft_plan_far_handled(d->eb_plan))
+            e = launch_update_e_b_foreign(d->k, d->lod_sources, d->stream, &l, eb_fft_plan_foreign_domain(d->eb_plan));
     } else {
         e = launch_update_e_b(d->k, d->lod_sources, d->stream, &l, d->deterministic);
     }

@@ -14,6 +14,16 @@
 namespace ion {
 using namespace ebfft;
 
+// one far slab's pyramid level: where it sits in QU_lod and how its centres are placed (sim.cl:960-972)
+struct FarDesc {
+    uint32_t entry0, nf;     // first QU_lod entry, sources per axis (2^level)
+    float bsx, bsy, bsz;     // block size of that level: N / 2^level (integer division, lod_coordinates sim.cl:440-447)
+    float shift_z;           // ddz * nz, halo layers included (quirk Q8)
+};
+struct FarDescs {
+    int n;
+    FarDesc d[8];
+};
 struct EbFftPlan {
     int nd;
     uint32_t ntasks;
@@ -25,8 +35,17 @@ struct EbFftPlan {
     Task* tasks;
     float2* khat;   // nsets * ntasks * khat_per_task
     float2* shat;   // nsets * shat_count
+    float2* shatc;  // compact spectrum of set 1 (odd-position symmetry), shatc_count
     float* scratch;  // the sums of a step before they are combined with the static fields: 6 floats per cell, rows permuted
     size_t khat_bytes;
+    // far slabs (two and more below): summed as a second-order Taylor polynomial per FARB^3 block of cells (eb_fft_core.cuh)
+    int far_n;               // number of far sources (0 = none); far_handled says whether this plan sums them
+    bool far_handled;
+    FarDesc far_desc[8];
+    int far_ndesc;
+    FarSource* far_src;
+    float* far_tens;         // [FAR_T][far_blocks]
+    uint32_t far_nbx, far_nby, far_nbz;
 };
 
 template <int ND>
@@ -45,14 +64,14 @@ __global__ void __launch_bounds__(256) k_eb_khat(const __grid_constant__ Geom g,
 
 template <int ND>
 __global__ void __launch_bounds__(128) k_eb_src(const __grid_constant__ Geom g, const __grid_constant__ SourceSet ss, const float* __restrict__ QU_lod,
-                                                 float2* __restrict__ shat) {
+                                                 float2* __restrict__ shat, float2* __restrict__ shatc) {
     __shared__ float2 plane[Cfg<ND>::M * Cfg<ND>::ROW];
     const int kx = blockIdx.x, j = blockIdx.y;
     src_phase_x<ND>(threadIdx.x, blockDim.x, g, ss, QU_lod, kx, j, plane);
     __syncthreads();
     src_phase_y<ND>(threadIdx.x, blockDim.x, plane);
     __syncthreads();
-    src_phase_z<ND>(threadIdx.x, blockDim.x, kx, j, plane, shat);
+    src_phase_z<ND>(threadIdx.x, blockDim.x, kx, j, plane, shat, shatc);
 }
 
 // ---- mbarrier + 1-D bulk copy (TMA engine, no registers, no issue slots per byte) ----
@@ -90,12 +109,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 template <int ND, int NSETS>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
-             const float2* __restrict__ khat2, const float2* __restrict__ shat2, float* __restrict__ scratch, const int accumulate) {
+             const float2* __restrict__ khat2, const float2* __restrict__ shat2c, float* __restrict__ scratch, const int accumulate) {
     typedef Cfg<ND> C;
     extern __shared__ __align__(128) unsigned char eb_smem[];
     __shared__ __align__(8) uint64_t bars[2];
     float2* W = reinterpret_cast<float2*>(eb_smem);  // [2][P][6][M][ROW]
-    float2* S0 = W + (size_t)2 * C::P * C::PLANE;     // s^_0 of the current planes [P][M][ROW] (single buffer, see below)
+    float2* S0 = W + (size_t)2 * C::P * C::PLANE;     // s^_0 of the current planes [P][M][ROW] (single buffer, see below);
+                                                      // NSETS = 2: the neighbour's compact spectrum [P][4][ND*ND] instead
     float2* tw = S0 + (size_t)C::P * C::SLOT;
     const int tid = threadIdx.x;
     if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
@@ -114,9 +134,14 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
         uint64_t* bar = &bars[it & 1];
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the targets were last touched by ordinary loads / stores
-        mbar_expect_tx(bar, (uint32_t)(np * (NSETS == 2 ? 6 : 7) * C::SLOT * sizeof(float2)));
+        mbar_expect_tx(bar, (uint32_t)(np * ((NSETS == 2 ? 6 : 7) * C::SLOT + (NSETS == 2 ? 4 * C::CSLOT : 0)) * sizeof(float2)));
         for (int p = 0; p < np; p++) {
             if (NSETS == 1) bulk_g2s(S0 + (size_t)p * C::SLOT, shat + ((size_t)kx0 + p) * C::SLOT, (uint32_t)(C::SLOT * sizeof(float2)), bar);
+            if (NSETS == 2) {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    bulk_g2s(S0 + ((size_t)p * 4 + j) * C::CSLOT, shat2c + ((size_t)j * C::H + kx0 + p) * C::CSLOT, (uint32_t)(C::CSLOT * sizeof(float2)), bar);
+            }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 bulk_g2s(Wb + (size_t)p * C::PLANE + (size_t)c * C::SLOT, kt + ((size_t)c * C::H + kx0 + p) * C::SLOT,
@@ -136,7 +161,7 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
         mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-        if (NSETS == 2) main_phase_product2<ND>(tid, shat, shat2, kx0, np, Wb);
+        if (NSETS == 2) main_phase_product2<ND>(tid, shat, S0, kx0, np, Wb);
         else main_phase_product<ND>(tid, S0, np, Wb);
         __syncthreads();
         // Every thread is past the x accumulation of iteration it - 1 (which read the other buffer) and past this iteration's
@@ -151,6 +176,46 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     main_phase_store<ND>(tid, g, t, scratch, accumulate != 0, acc);
 }
 
+// far sources of this step: (centre, q, q v) of every entry of the far slabs' pyramid levels, in the reference's order
+__global__ void k_eb_far_sources(const __grid_constant__ FarDescs fd, const float* __restrict__ QU_lod, FarSource* __restrict__ out) {
+    uint32_t base = 0;
+    for (int i = 0; i < fd.n; i++) {
+        const FarDesc& d = fd.d[i];
+        const uint32_t cnt = d.nf * d.nf * d.nf;
+        for (uint32_t k = threadIdx.x; k < cnt; k += blockDim.x) {
+            const uint32_t t = k % (d.nf * d.nf);
+            const float4 v = reinterpret_cast<const float4*>(QU_lod)[d.entry0 + k];
+            FarSource s;
+            s.cx = (float)(t % d.nf) * d.bsx + 0.5f * d.bsx;
+            s.cy = (float)(t / d.nf) * d.bsy + 0.5f * d.bsy;
+            s.cz = ((float)(k / (d.nf * d.nf)) * d.bsz + 0.5f * d.bsz) - d.shift_z;
+            s.q = v.x;
+            s.wx = v.y * v.x; s.wy = v.z * v.x; s.wz = v.w * v.x;
+            s.pad = 0.0f;
+            out[base + k] = s;
+        }
+        base += cnt;
+    }
+}
+// Taylor tensors of the far field, one thread per FARB^3 block of cells
+__global__ void __launch_bounds__(128) k_eb_far_tensors(const FarSource* __restrict__ src, const int nsrc, float* __restrict__ tens, const uint32_t nbx,
+                                                         const uint32_t nby, const uint32_t nbz) {
+    __shared__ FarSource s_src[128];
+    for (int k = threadIdx.x; k < nsrc; k += blockDim.x) s_src[k] = src[k];
+    __syncthreads();
+    const uint32_t nblocks = nbx * nby * nbz;
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblocks) return;
+    const uint32_t bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
+    const float c = 0.5f * (float)(FARB - 1);
+    float t[FAR_T];
+#pragma unroll
+    for (int i = 0; i < FAR_T; i++) t[i] = 0.0f;
+    for (int k = 0; k < nsrc; k++) far_accumulate((float)(bx * FARB) + c, (float)(by * FARB) + c, (float)(bz * FARB) + c, s_src[k], t);
+#pragma unroll
+    for (int i = 0; i < FAR_T; i++) tens[(size_t)i * nblocks + b] = t[i];
+}
+
 // E_dyn = E_stat + KE * e, B_dyn = B_stat + KMU * b (sim.cl:986-992): one block per row (y, z), everything coalesced.  A thread
 // owns CH cells of the row (x = threadIdx.x + k * blockDim.x); all 13 loads per cell (6 scratch components, flag, 6 static
 // components) are in flight before the first is used; the scratch values pass through shared memory, which undoes the row
@@ -159,13 +224,22 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
 template <int ND, int CH>
 __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom g, const float* __restrict__ scratch, const uint8_t* __restrict__ flags,
                                                      const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
-                                                     float* __restrict__ B_dyn) {
+                                                     float* __restrict__ B_dyn, const float* __restrict__ far_tens, const uint32_t far_nbx,
+                                                     const uint32_t far_blocks) {
     extern __shared__ __align__(128) unsigned char eb_smem[];
     float* tile = reinterpret_cast<float*>(eb_smem);  // [6][tile_len]
     const uint32_t y = blockIdx.x, z = blockIdx.y;
     if (((g.dy > 1u) & (y == 0u || y >= g.ny - 1u)) || ((g.dz > 1u) & (z == 0u || z >= g.nz - 1u))) return;  // halo rows, sim.cl:899
     const uint32_t tile_len = (g.nx / ND) * (ND + 1) + ND + 1;
     const uint64_t base = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
+    // far slabs: the Taylor tensors of this row's FARB^3 blocks ([FAR_T][far_nbx] floats, after the six permuted rows)
+    float* ftile = tile + (size_t)6 * tile_len;
+    const float fdy = (float)(y % FARB) - 0.5f * (float)(FARB - 1), fdz = (float)(z % FARB) - 0.5f * (float)(FARB - 1);
+    if (far_tens) {
+        const uint32_t brow = (y / FARB + (g.ny + FARB - 1u) / FARB * (z / FARB)) * far_nbx;
+        for (uint32_t i = threadIdx.x; i < (uint32_t)FAR_T * far_nbx; i += blockDim.x)
+            ftile[i] = far_tens[(size_t)(i / far_nbx) * far_blocks + brow + i % far_nbx];
+    }
     constexpr int R = CH > 0 ? CH : 1;
     float st[R][6];
     uint8_t fl[R];
@@ -205,10 +279,24 @@ __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom
             if (x >= g.nx || ((g.dx > 1u) & (x == 0u || x >= g.nx - 1u))) continue;  // is_halo, sim.cl:899
             if ((fl[k] & 0x1Fu) == 0x01u) continue;                                   // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
             const uint32_t p = (x % g.dsx) * (ND + 1) + x / g.dsx;
+            float sum[6];
+#pragma unroll
+            for (int c = 0; c < 6; c++) sum[c] = tile[(size_t)c * tile_len + p];
+            if (far_tens) {  // + the far slabs' field, evaluated from the block's Taylor polynomial
+                float t[FAR_T];
+#pragma unroll
+                for (int i = 0; i < FAR_T; i++) t[i] = ftile[(size_t)i * far_nbx + x / FARB];
+                const float fdx = (float)(x % FARB) - 0.5f * (float)(FARB - 1);
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    sum[c] += far_eval(t, c, fdx, fdy, fdz);
+                    sum[3 + c] += far_eval(t + 30, c, fdx, fdy, fdz);
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 3; c++) {
-                E_dyn[(uint64_t)c * g.N + base + x] = st[k][c] + g.ke * tile[(size_t)c * tile_len + p];
-                B_dyn[(uint64_t)c * g.N + base + x] = st[k][3 + c] + g.kmu * tile[(size_t)(3 + c) * tile_len + p];
+                E_dyn[(uint64_t)c * g.N + base + x] = st[k][c] + g.ke * sum[c];
+                B_dyn[(uint64_t)c * g.N + base + x] = st[k][3 + c] + g.kmu * sum[3 + c];
             }
         }
     } else {
@@ -274,7 +362,10 @@ void eb_fft_destroy(EbFftPlan* p) {
     if (p->tasks) cudaFree(p->tasks);
     if (p->khat) cudaFree(p->khat);
     if (p->shat) cudaFree(p->shat);
+    if (p->shatc) cudaFree(p->shatc);
     if (p->scratch) cudaFree(p->scratch);
+    if (p->far_src) cudaFree(p->far_src);
+    if (p->far_tens) cudaFree(p->far_tens);
     delete p;
 }
 
@@ -310,6 +401,38 @@ static void foreign_set(const KArgs& a, const Geom& g, EbFftPlan* p) {
     p->foreign_domain = (int)a.di - 1;
 }
 
+// Far slabs: domains two and more below this one (z slabs; the ones above are skipped like everywhere in the fast paths, quirk Q18).
+// Fills the descriptors and decides whether the Taylor path may sum them: every (cell, source) distance must be at least
+// 40 x the largest offset inside a FARB^3 block, which bounds the truncation error by 1.6e-5 of the far field.
+static void far_set(const KArgs& a, EbFftPlan* p) {
+    p->far_n = 0;
+    p->far_ndesc = 0;
+    p->far_handled = false;
+    if (p->foreign_domain < 0 || a.di < 2u) return;  // no far slab, or the neighbour is not on the FFT path either
+    bool ok = a.nx <= 2048u && a.di - 1u <= 8u;
+    uint32_t entry = a.n_lod_own;
+    const float dmax = 0.5f * (float)(FARB - 1) * 1.7320508f;
+    for (uint32_t d = 0; d + 1u < a.di; d++) {
+        const uint32_t ddz = a.di - d;
+        const int level = (int)a.lod_depth - (int)ddz > 0 ? (int)a.lod_depth - (int)ddz : 0;
+        const uint32_t nf = 1u << level;
+        if (ok) {
+            FarDesc& f = p->far_desc[p->far_ndesc++];
+            f.entry0 = entry;
+            f.nf = nf;
+            f.bsx = (float)(a.nx / nf); f.bsy = (float)(a.ny / nf); f.bsz = (float)(a.nz / nf);
+            f.shift_z = (float)(ddz * a.nz);
+            const float top = ((float)(nf - 1u) * f.bsz + 0.5f * f.bsz) - f.shift_z;  // highest centre of this slab's level
+            if (1.0f - top < 40.0f * dmax) ok = false;                                // the lowest cell a slab updates is z = 1
+            p->far_n += (int)(nf * nf * nf);
+        }
+        entry += nf * nf * nf;
+    }
+    if (p->far_n > 128) ok = false;
+    p->far_handled = ok && p->far_n > 0;
+    if (!p->far_handled) { p->far_n = 0; p->far_ndesc = 0; }
+}
+
 // Builds the static part (task list, K^) on the domain's device.  *out = nullptr (and cudaSuccess) when the geometry is not
 // supported or the spectra do not fit `budget_bytes`.
 cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, EbFftPlan** out, uint64_t* launches) {
@@ -317,7 +440,8 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     if (!eb_fft_supported(a)) return cudaSuccess;
     EbFftPlan* p = new EbFftPlan();
     p->nd = 1 << a.lod_depth;
-    p->tasks = nullptr; p->khat = nullptr; p->shat = nullptr; p->scratch = nullptr;
+    p->tasks = nullptr; p->khat = nullptr; p->shat = nullptr; p->shatc = nullptr; p->scratch = nullptr;
+    p->far_src = nullptr; p->far_tens = nullptr; p->far_n = 0; p->far_handled = false; p->far_ndesc = 0;
     std::vector<Task> tasks;
     eb_fft_geometry(a, p->g, tasks);
     p->ntasks = (uint32_t)tasks.size();
@@ -334,9 +458,15 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
         p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
     }
     if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
+    far_set(a, p);
+    p->far_nbx = (a.nx + FARB - 1u) / FARB; p->far_nby = (a.ny + FARB - 1u) / FARB; p->far_nbz = (a.nz + FARB - 1u) / FARB;
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
+    if (e == cudaSuccess && p->far_handled) e = cudaMalloc((void**)&p->far_src, 128 * sizeof(FarSource));
+    if (e == cudaSuccess && p->far_handled) e = cudaMalloc((void**)&p->far_tens, (size_t)FAR_T * p->far_nbx * p->far_nby * p->far_nbz * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->khat, p->khat_bytes);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->shat, (size_t)p->nsets * sh * sizeof(float2));
+    if (e == cudaSuccess && p->nsets == 2)
+        e = cudaMalloc((void**)&p->shatc, (p->nd == 16 ? Cfg<16>::shatc_count : Cfg<8>::shatc_count) * sizeof(float2));
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->scratch, scratch_bytes);
     if (e == cudaSuccess) e = cudaMemcpyAsync(p->tasks, tasks.data(), tasks.size() * sizeof(Task), cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);  // `tasks` is a local vector
@@ -358,13 +488,22 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     if (e != cudaSuccess) return e;
     const size_t kstride = (size_t)p->ntasks * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
     for (int set = 0; set < p->nsets; set++)
-        k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride);
+        k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride, set == 1 ? p->shatc : nullptr);
     if (p->nsets == 2)
-        k_eb_fft<ND, 2><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->khat + kstride, p->shat + sstride, p->scratch, 0);
+        k_eb_fft<ND, 2><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->khat + kstride, p->shatc, p->scratch, 0);
     else
         k_eb_fft<ND, 1><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
+    const uint32_t far_blocks = p->far_nbx * p->far_nby * p->far_nbz;
+    if (p->far_handled) {
+        FarDescs fd;
+        fd.n = p->far_ndesc;
+        for (int i = 0; i < fd.n; i++) fd.d[i] = p->far_desc[i];
+        k_eb_far_sources<<<1, 128, 0, s>>>(fd, a.QU_lod, p->far_src);
+        k_eb_far_tensors<<<(far_blocks + 127u) / 128u, 128, 0, s>>>(p->far_src, p->far_n, p->far_tens, p->far_nbx, p->far_nby, p->far_nbz);
+    }
+    const float* far_tens = p->far_handled ? p->far_tens : nullptr;
     const uint32_t tile_len = (a.nx / ND) * (ND + 1) + ND + 1;
-    const size_t csmem = (size_t)6 * tile_len * sizeof(float);
+    const size_t csmem = (size_t)6 * tile_len * sizeof(float) + (p->far_handled ? (size_t)FAR_T * p->far_nbx * sizeof(float) : 0);
     const uint32_t threads = a.nx < 256u ? ((a.nx + 31u) / 32u) * 32u : 256u;
     const uint32_t chunks = (a.nx + threads - 1u) / threads;
     const dim3 grid(a.ny, a.nz);
@@ -374,7 +513,8 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
             e = cudaFuncSetAttribute(k_eb_combine<ND, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);               \
             if (e != cudaSuccess) return e;                                                                                        \
         }                                                                                                                          \
-        k_eb_combine<ND, CH><<<grid, threads, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn);         \
+        k_eb_combine<ND, CH><<<grid, threads, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn, far_tens, \
+                                                          p->far_nbx, far_blocks);                                                  \
     } while (0)
     if (chunks <= 1u) ION_COMBINE(1);
     else if (chunks <= 2u) ION_COMBINE(2);
@@ -385,11 +525,12 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    *launches += 2u + (uint64_t)p->nsets;
+    *launches += 2u + (uint64_t)p->nsets + (p->far_handled ? 2u : 0u);
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }
 int eb_fft_plan_foreign_domain(const EbFftPlan* p) { return p ? p->foreign_domain : -1; }
+bool eb_fft_plan_far_handled(const EbFftPlan* p) { return p && p->far_handled; }
 size_t eb_fft_scratch_bytes(const EbFftPlan* p) { return p ? (size_t)6 * p->g.N * sizeof(float) : 0; }
 uint32_t eb_fft_plan_tasks(const EbFftPlan* p) { return p ? p->ntasks : 0; }
 

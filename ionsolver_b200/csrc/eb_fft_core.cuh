@@ -83,6 +83,10 @@ template <int ND> struct Cfg {
     static constexpr size_t shat_count = (size_t)4 * H * SLOT;     // float2
     // work buffers [2][P][6 slots] + s^_0 staging [P slots] + x twiddles
     static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + (size_t)P * SLOT * sizeof(float2) + M * sizeof(float2);
+    // compact spectrum of a source set that lives on the ODD grid positions only (kind 1): s^(k + ND e_a) = -s^(k) on every axis, so
+    // ND x ND values per (component, kx) describe the whole M x M plane
+    static constexpr int CSLOT = ND * ND;
+    static constexpr size_t shatc_count = (size_t)4 * H * CSLOT;
     static constexpr size_t khat_smem = (size_t)H * M * ROW * sizeof(float2);
     static constexpr size_t src_smem = (size_t)M * ROW * sizeof(float2);
 };
@@ -296,7 +300,7 @@ template <int ND> ION_HD void src_phase_y(int tid, int nthreads, float2* plane) 
     }
 }
 // layout of s^: [j][kx][kz][ROW] (same padded rows as K^)
-template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, const float2* plane, float2* shat) {
+template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, const float2* plane, float2* shat, float2* shatc) {
     typedef Cfg<ND> C;
     for (int ky = tid; ky < C::M; ky += nthreads) {
         float2 a[C::M];
@@ -306,6 +310,11 @@ template <int ND> ION_HD void src_phase_z(int tid, int nthreads, int kx, int j, 
         float2* out = shat + ((size_t)j * C::H + kx) * C::SLOT + ky;
 #pragma unroll
         for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::ROW] = a[kz];
+        if (shatc && ky < ND) {  // compact copy [j][kx][kz < ND][ky < ND] for the sets with the odd-position symmetry
+            float2* oc = shatc + ((size_t)j * C::H + kx) * C::CSLOT + ky;
+#pragma unroll
+            for (int kz = 0; kz < ND; kz++) oc[(size_t)kz * ND] = a[kz];
+        }
     }
 }
 
@@ -355,40 +364,65 @@ template <int ND> ION_HD void main_phase_product(int tid, const float2* S0, int 
     }
 }
 // phase 1 with TWO source sets (a slab with a lower neighbour): K^ of the own level was staged in the E slots, K^' of the
-// neighbour's level D-1 in the B slots; both source spectra come from L2.  The spectra of the two convolutions are ADDED here,
-// so that one inverse transform serves both (the transform is linear) -- the second set costs products, not FFTs.
-template <int ND> ION_HD void main_phase_product2(int tid, const float2* shat, const float2* shat2, int kx0, int np, float2* W) {
+// neighbour's level D-1 in the B slots; the own source spectrum comes from L2 (loads batched three points deep), the neighbour's
+// from its compact staged form S2c[P][4][ND*ND].  The spectra of the two convolutions are ADDED here, so that one inverse transform
+// serves both (the transform is linear) -- the second set costs products, not FFTs.
+template <int ND> ION_HD void main_phase_product2(int tid, const float2* shat, const float2* S2c, int kx0, int np, float2* W) {
     typedef Cfg<ND> C;
     constexpr int MM = C::M * C::M;
     constexpr size_t CS = (size_t)C::H * C::SLOT;  // component stride of s^
-#pragma unroll 2
-    for (int idx = tid; idx < np * MM; idx += C::T) {
-        const int p = idx / MM, f = idx % MM;
-        const int kz = f / C::M, ky = f % C::M;
-        const int o = kz * C::ROW + ky;
-        const size_t gi = (size_t)(kx0 + p) * C::SLOT + o;
-        float2* w = W + (size_t)p * C::PLANE + o;
-        const float2 s0 = ION_LDG2(shat + gi), s1 = ION_LDG2(shat + CS + gi), s2 = ION_LDG2(shat + 2 * CS + gi), s3 = ION_LDG2(shat + 3 * CS + gi);
-        const float2 t0 = ION_LDG2(shat2 + gi), t1 = ION_LDG2(shat2 + CS + gi), t2 = ION_LDG2(shat2 + 2 * CS + gi), t3 = ION_LDG2(shat2 + 3 * CS + gi);
-        const float2 k0 = w[0], k1 = w[C::SLOT], k2 = w[2 * C::SLOT];
-        const float2 l0 = w[3 * C::SLOT], l1 = w[4 * C::SLOT], l2 = w[5 * C::SLOT];
-        float2 E[3], B[3];
-        E[0] = cmul(k0, s0); E[1] = cmul(k1, s0); E[2] = cmul(k2, s0);
-        B[0] = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
-        B[1] = cmul_sub(s3, k0, s1, k2);
-        B[2] = cmul_sub(s1, k1, s2, k0);
-        const float2 e0 = cmul(l0, t0), e1 = cmul(l1, t0), e2 = cmul(l2, t0);
-        const float2 b0 = cmul_sub(t2, l2, t3, l1), b1 = cmul_sub(t3, l0, t1, l2), b2 = cmul_sub(t1, l1, t2, l0);
-        w[0] = make_float2(E[0].x + e0.x, E[0].y + e0.y);
-        w[C::SLOT] = make_float2(E[1].x + e1.x, E[1].y + e1.y);
-        w[2 * C::SLOT] = make_float2(E[2].x + e2.x, E[2].y + e2.y);
-        w[3 * C::SLOT] = make_float2(B[0].x + b0.x, B[0].y + b0.y);
-        w[4 * C::SLOT] = make_float2(B[1].x + b1.x, B[1].y + b1.y);
-        w[5 * C::SLOT] = make_float2(B[2].x + b2.x, B[2].y + b2.y);
+    constexpr int B = 3;                           // points per batch: all loads of a batch are in flight before the first product
+    for (int idx0 = tid; idx0 < np * MM; idx0 += B * C::T) {
+        float2 sv[B][4];
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+            const int idx = idx0 + u * C::T;
+            if (idx < np * MM) {
+                const int p = idx / MM, f = idx % MM;
+                const size_t gi = (size_t)(kx0 + p) * C::SLOT + (f / C::M) * C::ROW + f % C::M;
+#pragma unroll
+                for (int j = 0; j < 4; j++) sv[u][j] = ION_LDG2(shat + (size_t)j * CS + gi);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < B; u++) {
+            const int idx = idx0 + u * C::T;
+            if (idx >= np * MM) continue;
+            const int p = idx / MM, f = idx % MM;
+            const int kz = f / C::M, ky = f % C::M;
+            float2* w = W + (size_t)p * C::PLANE + kz * C::ROW + ky;
+            // s^' from its compact form: sign flips when kz or ky leaves [0, ND)
+            const float sg = ((kz >= ND) != (ky >= ND)) ? -1.0f : 1.0f;
+            const float2* c2 = S2c + (size_t)p * 4 * C::CSLOT + (kz & (ND - 1)) * ND + (ky & (ND - 1));
+            float2 t[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float2 v = c2[(size_t)j * C::CSLOT];
+                t[j] = make_float2(sg * v.x, sg * v.y);
+            }
+            const float2 s0 = sv[u][0], s1 = sv[u][1], s2 = sv[u][2], s3 = sv[u][3];
+            const float2 k0 = w[0], k1 = w[C::SLOT], k2 = w[2 * C::SLOT];
+            const float2 l0 = w[3 * C::SLOT], l1 = w[4 * C::SLOT], l2 = w[5 * C::SLOT];
+            const float2 E0 = cmul(k0, s0), E1 = cmul(k1, s0), E2 = cmul(k2, s0);
+            const float2 B0 = cmul_sub(s2, k2, s3, k1);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
+            const float2 B1 = cmul_sub(s3, k0, s1, k2);
+            const float2 B2 = cmul_sub(s1, k1, s2, k0);
+            const float2 e0 = cmul(l0, t[0]), e1 = cmul(l1, t[0]), e2 = cmul(l2, t[0]);
+            const float2 b0 = cmul_sub(t[2], l2, t[3], l1), b1 = cmul_sub(t[3], l0, t[1], l2), b2 = cmul_sub(t[1], l1, t[2], l0);
+            w[0] = make_float2(E0.x + e0.x, E0.y + e0.y);
+            w[C::SLOT] = make_float2(E1.x + e1.x, E1.y + e1.y);
+            w[2 * C::SLOT] = make_float2(E2.x + e2.x, E2.y + e2.y);
+            w[3 * C::SLOT] = make_float2(B0.x + b0.x, B0.y + b0.y);
+            w[4 * C::SLOT] = make_float2(B1.x + b1.x, B1.y + b1.y);
+            w[5 * C::SLOT] = make_float2(B2.x + b2.x, B2.y + b2.y);
+        }
     }
 }
-template <int ND> inline void main_stage2_host(const float2* khat_task, const float2* khat2_task, int kx0, int np, float2* W) {
+template <int ND> inline void main_stage2_host(const float2* khat_task, const float2* khat2_task, const float2* shat2c, int kx0, int np, float2* W, float2* S2c) {
     typedef Cfg<ND> C;
+    for (int p = 0; p < np; p++)
+        for (int j = 0; j < 4; j++)
+            for (int i = 0; i < C::CSLOT; i++) S2c[((size_t)p * 4 + j) * C::CSLOT + i] = shat2c[((size_t)j * C::H + kx0 + p) * C::CSLOT + i];
     for (int p = 0; p < np; p++)
         for (int c = 0; c < 3; c++)
             for (int i = 0; i < C::SLOT; i++) {
@@ -497,6 +531,74 @@ ION_HD void combine_write(int tid, int nthreads, const Geom& g, uint32_t y, uint
         if ((flags[base + x] & 0x1Fu) == 0x01u) continue;         // (flags & TYPE_BO) == TYPE_S, sim.cl:900-902
         dyn[x] = stat[x] + k * tile[(x % g.dsx) * (ND + 1) + x / g.dsx];
     }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Far slabs (sim.cl:957-983, domains two and more slabs below): at most 8^(D-2) + 8^(D-3) + ... sources, hundreds of cells away.
+// Their field varies slowly over a few cells, so it is summed ONCE per FARB^3 block of cells as a second-order Taylor polynomial
+// about the block centre (value, gradient, Hessian of q f(r) and w x f(r), f = r/|r|^3) and every cell evaluates the polynomial:
+// the cost per cell no longer depends on the number of far sources.  Truncation error relative to the far field itself is
+// (|delta| / R)^3 with |delta| <= 2.6 cells; the host enables the path only when R >= 40 |delta| for every (cell, source) pair,
+// i.e. below 1.6e-5 of a contribution that is itself a fraction of the field (otherwise the direct kernel sums these sources).
+// Table layout: tens[FAR_T][nblocks], block index bx + nbx * (by + nby * bz); entries 0..29 = E part, 30..59 = B part, each
+// F0[3] | G[3][3] | H[3][6] with the pair order (xx, xy, xz, yy, yz, zz).
+// ------------------------------------------------------------------------------------------------------
+constexpr int FARB = 4;
+constexpr int FAR_T = 60;
+struct FarSource {
+    float cx, cy, cz, q;
+    float wx, wy, wz, pad;
+};
+ION_HD int far_pair(int l, int m) {  // index of the symmetric pair (l, m)
+    const int a = l < m ? l : m, b = l < m ? m : l;
+    return a == 0 ? b : (a == 1 ? 2 + b : 5);
+}
+// accumulates one source into the 60 tensor entries of the block centred at (x0, y0, z0)
+ION_HD void far_accumulate(float x0, float y0, float z0, const FarSource& s, float (&t)[FAR_T]) {
+    const float r[3] = {x0 - s.cx, y0 - s.cy, z0 - s.cz};
+    const float R2 = fmaf(r[0], r[0], fmaf(r[1], r[1], r[2] * r[2]));
+    const float inv = 1.0f / sqrtf(R2), inv2 = inv * inv, inv3 = inv * inv2, inv5 = inv3 * inv2, inv7 = inv5 * inv2;
+    float f[3], df[3][3], d2[3][6];
+    const float w[3] = {s.wx, s.wy, s.wz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        f[k] = r[k] * inv3;
+#pragma unroll
+        for (int l = 0; l < 3; l++) df[k][l] = (k == l ? inv3 : 0.0f) - 3.0f * r[k] * r[l] * inv5;
+#pragma unroll
+        for (int l = 0; l < 3; l++)
+#pragma unroll
+            for (int m = l; m < 3; m++)
+                d2[k][far_pair(l, m)] = -3.0f * ((k == l ? r[m] : 0.0f) + (k == m ? r[l] : 0.0f) + (l == m ? r[k] : 0.0f)) * inv5 +
+                                        15.0f * r[k] * r[l] * r[m] * inv7;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;  // (w x f)_i = w_j f_k - w_k f_j
+        t[i] = fmaf(s.q, f[i], t[i]);
+        t[30 + i] += w[j] * f[k] - w[k] * f[j];
+#pragma unroll
+        for (int l = 0; l < 3; l++) {
+            t[3 + 3 * i + l] = fmaf(s.q, df[i][l], t[3 + 3 * i + l]);
+            t[33 + 3 * i + l] += w[j] * df[k][l] - w[k] * df[j][l];
+        }
+#pragma unroll
+        for (int p = 0; p < 6; p++) {
+            t[12 + 6 * i + p] = fmaf(s.q, d2[i][p], t[12 + 6 * i + p]);
+            t[42 + 6 * i + p] += w[j] * d2[k][p] - w[k] * d2[j][p];
+        }
+    }
+}
+// value of component i (0..2 = E, 3..5 = B) of the polynomial at offset (dx, dy, dz) from the block centre; `t` = the 30 entries of
+// the E or B part
+ION_HD float far_eval(const float* t, int i, float dx, float dy, float dz) {
+    const float* G = t + 3 + 3 * i;
+    const float* H = t + 12 + 6 * i;
+    float v = t[i];
+    v = fmaf(G[0], dx, fmaf(G[1], dy, fmaf(G[2], dz, v)));
+    v = fmaf(0.5f * H[0], dx * dx, fmaf(H[1], dx * dy, fmaf(H[2], dx * dz, v)));
+    v = fmaf(0.5f * H[3], dy * dy, fmaf(H[4], dy * dz, fmaf(0.5f * H[5], dz * dz, v)));
+    return v;
 }
 
 }  // namespace ebfft

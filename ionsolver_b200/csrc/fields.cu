@@ -980,9 +980,15 @@ cudaError_t launch_update_e_b_foreign(const KArgs& a, void* scratch_sources, cud
     const uint32_t nd = 1u << a.lod_depth;
     const uint32_t own = nd * nd * nd;
     if (count <= own) return cudaSuccess;  // single domain
-    if (skip_domain >= 0) {  // anything left?  (slabs above are skipped by the fast path: quirk Q18)
-        bool any = false;
-        for (uint32_t d = 0; d < a.di && !any; d++) any = (int)d != skip_domain;
+    {  // anything left to sum?  Domains whose centre shift wraps through the uint product (quirk Q18) are skipped by the fast path,
+       // and `skip_domain` is already in E_dyn / B_dyn: the first slab of a z decomposition has nothing to do here
+        ForeignSet fs;
+        describe_foreign(a, nd, fs, skip_domain);
+        bool any = fs.n == 0u;  // too many domains for descriptors: the kernel walks the flat table
+        for (uint32_t i = 0; i < fs.n && !any; i++) {
+            const ForeignDesc& f = fs.d[i];
+            any = f.fast != 2u && !(fabsf(f.sx) > ION_FAR_SHIFT || fabsf(f.sy) > ION_FAR_SHIFT || fabsf(f.sz) > ION_FAR_SHIFT);
+        }
         if (!any) return cudaSuccess;
     }
     LodSource* src = reinterpret_cast<LodSource*>(scratch_sources);

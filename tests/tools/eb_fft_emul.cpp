@@ -69,6 +69,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     for (int i = 0; i < C::M; i++) tw[i] = make_float2(tw_cos32(i * (32 / C::M)), tw_sin32(i * (32 / C::M)));
     std::vector<float> accreg((size_t)C::T * 6 * C::XPT);
     std::vector<float2> khat2(nsets == 2 ? C::khat_per_task * ntasks : 0), shat2(nsets == 2 ? C::shat_count : 0);
+    std::vector<float2> shat2c(nsets == 2 ? C::shatc_count : 0), S2c((size_t)C::P * 4 * C::CSLOT);
     for (int set = 0; set < nsets; set++) {
         float2* kh = set == 0 ? khat.data() : khat2.data();
         float2* sh = set == 0 ? shat.data() : shat2.data();
@@ -82,7 +83,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
             for (int kx = 0; kx < C::H; kx++) {
                 for (int tid = 0; tid < 128; tid++) src_phase_x<ND>(tid, 128, g, sets[set], lod.data(), kx, j, plane.data());
                 for (int tid = 0; tid < 128; tid++) src_phase_y<ND>(tid, 128, plane.data());
-                for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), sh);
+                for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), sh, set == 1 ? shat2c.data() : nullptr);
             }
     }
     for (int t = 0; t < ntasks; t++) {  // one pass: with two source sets their spectra are added before the inverse transform
@@ -91,8 +92,8 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
         for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
             const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
             if (nsets == 2) {
-                main_stage2_host<ND>(kt, khat2.data() + C::khat_per_task * t, kx0, np, W.data());
-                for (int tid = 0; tid < C::T; tid++) main_phase_product2<ND>(tid, shat.data(), shat2.data(), kx0, np, W.data());
+                main_stage2_host<ND>(kt, khat2.data() + C::khat_per_task * t, shat2c.data(), kx0, np, W.data(), S2c.data());
+                for (int tid = 0; tid < C::T; tid++) main_phase_product2<ND>(tid, shat.data(), S2c.data(), kx0, np, W.data());
             } else {
                 main_stage_host<ND>(kt, shat.data(), kx0, np, W.data(), S0.data());
                 for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, S0.data(), np, W.data());
