@@ -154,6 +154,9 @@ ION_API int ion_read_slice(ion_domain_t* dom, int field, int component, uint32_t
 /* kernels: one per enqueue site ---------------------------------------------------------------------------- */
 ION_API int ion_enqueue_initialize(ion_domain_t* dom);                                          /* domain.rs:412-416 (ends with finish) */
 ION_API int ion_enqueue_stream_collide(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz); /* domain.rs:419-428 */
+/* the same kernel on the z layers [z_begin, z_end) only -- boundary-layer-first scheduling: launch the two layers next to the halos,
+ * start the halo exchange on the halo stream (ion_halo_fork), launch the interior; finish != 0 on the LAST range of a step (LOD fold) */
+ION_API int ion_enqueue_stream_collide_range(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz, uint32_t z_begin, uint32_t z_end, int finish);
 ION_API int ion_enqueue_update_fields(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz);  /* domain.rs:432-441 */
 ION_API int ion_enqueue_update_e_b_dyn(ion_domain_t* dom);                                      /* domain.rs:443-451 */
 /* no reference counterpart: 0 (default) = psi_from_mesh with the reference's arithmetic and summation order (B_stat bit-identical to the

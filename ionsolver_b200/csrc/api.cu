@@ -505,16 +505,26 @@ int ion_enqueue_initialize(ion_domain_t* d) {
     return ION_OK;
 }
 
-int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, float fz) {
+// z layers [z_begin, z_end) of stream_collide; `finish` = this is the last range of the step: fold the LOD deposits (or sum them in
+// order in the deterministic mode), which needs every layer done.  Esoteric-Pull makes the order of the ranges irrelevant: a thread
+// reads and writes only its own set of (cell, slot) addresses (sim_kernels.cl:234-247).
+static int stream_collide_range(ion_domain_t* d, uint64_t t, float fx, float fy, float fz, uint32_t z_begin, uint32_t z_end, bool finish) {
     if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    if (z_begin > z_end || z_end > d->params.nz) return fail(ION_ERR_RANGE, "z range [%u, %u) outside the domain (%u layers)", z_begin, z_end, d->params.nz);
     ION_CUDA(cudaSetDevice(d->device));
-    cudaError_t e;
+    cudaError_t e = cudaSuccess;
     const bool mhd = d->params.ext & ION_EXT_MAGNETO_HYDRO;
     const bool trt = d->params.relaxation_time == ION_TRT;
     const bool ecr = d->params.ext & ION_EXT_SUBGRID_ECR;
-    ION_VS_DISPATCH(launch_stream_collide_vs, d->k, (int)d->params.float_type, mhd, trt, ecr, t, fx, fy, fz, d->stream)
-    g_launches++;
-    if (e != cudaSuccess) return cuda_fail(e, "stream_collide launch");
+    if (z_end > z_begin) {
+        KArgs k = d->k;
+        k.z_off = z_begin;
+        k.z_cnt = (z_begin == 0u && z_end == d->params.nz) ? 0u : z_end - z_begin;
+        ION_VS_DISPATCH(launch_stream_collide_vs, k, (int)d->params.float_type, mhd, trt, ecr, t, fx, fy, fz, d->stream)
+        g_launches++;
+        if (e != cudaSuccess) return cuda_fail(e, "stream_collide launch");
+    }
+    if (!finish) return ION_OK;
     if (mhd && d->deterministic && d->params.lod_depth > 0u) {  // ordered LOD sums instead of the in-kernel float atomics
         e = launch_lod_deposit_ordered(d->k, d->stream);
         g_launches++;
@@ -525,6 +535,13 @@ int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, 
         if (e != cudaSuccess) return cuda_fail(e, "lod_fold launch");
     }
     return ION_OK;
+}
+int ion_enqueue_stream_collide(ion_domain_t* d, uint64_t t, float fx, float fy, float fz) {
+    if (!d) return fail(ION_ERR_INVALID, "NULL domain");
+    return stream_collide_range(d, t, fx, fy, fz, 0u, d->params.nz, true);
+}
+int ion_enqueue_stream_collide_range(ion_domain_t* d, uint64_t t, float fx, float fy, float fz, uint32_t z_begin, uint32_t z_end, int finish) {
+    return stream_collide_range(d, t, fx, fy, fz, z_begin, z_end, finish != 0);
 }
 
 int ion_enqueue_update_fields(ion_domain_t* d, uint64_t t, float fx, float fy, float fz) {

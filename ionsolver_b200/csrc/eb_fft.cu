@@ -6,6 +6,7 @@
 //   k_eb_fft   (every step)         one block per task: products, 2-D inverse FFT in shared memory, Hermitian DFT along x,
 //                                   E_dyn / B_dyn = static + k * sum   (sim.cl:986-992)
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "eb_fft_core.cuh"
@@ -459,6 +460,12 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     }
     if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
     far_set(a, p);
+    {  // room for the pinned source spectra in L2 (a device-wide limit; a few MB of 126)
+        size_t cur = 0;
+        if (cudaDeviceGetLimit(&cur, cudaLimitPersistingL2CacheSize) != cudaSuccess || cur < (size_t)8 << 20) {
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)8 << 20) != cudaSuccess) cudaGetLastError();
+        }
+    }
     p->far_nbx = (a.nx + FARB - 1u) / FARB; p->far_nby = (a.ny + FARB - 1u) / FARB; p->far_nbz = (a.nz + FARB - 1u) / FARB;
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
     if (e == cudaSuccess && p->far_handled) e = cudaMalloc((void**)&p->far_src, 128 * sizeof(FarSource));
@@ -481,6 +488,21 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     return cudaSuccess;
 }
 
+// The source spectra (1-2 MB) are read by every block of k_eb_fft while 2-4 GB of kernel spectra stream through L2 once: pin them
+// with a persisting access-policy window for the duration of the kernel so that the stream does not evict them.
+static void pin_source_spectra(const EbFftPlan* p, cudaStream_t s, size_t bytes, bool on) {
+    static const bool enabled = !(getenv("ION_EB_L2PIN") && atoi(getenv("ION_EB_L2PIN")) == 0);
+    if (!enabled) return;
+    cudaStreamAttrValue v;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = (void*)p->shat;
+    v.accessPolicyWindow.num_bytes = on ? bytes : 0;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = on ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();  // best effort
+}
+
 template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& a, cudaStream_t s) {
     // function attributes are per device: set on every launch (a host-side table lookup)
     cudaError_t e = p->nsets == 2 ? cudaFuncSetAttribute(k_eb_fft<ND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem)
@@ -489,10 +511,12 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     const size_t kstride = (size_t)p->ntasks * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
     for (int set = 0; set < p->nsets; set++)
         k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride, set == 1 ? p->shatc : nullptr);
+    pin_source_spectra(p, s, (size_t)p->nsets * sstride * sizeof(float2), true);
     if (p->nsets == 2)
         k_eb_fft<ND, 2><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->khat + kstride, p->shatc, p->scratch, 0);
     else
         k_eb_fft<ND, 1><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
+    pin_source_spectra(p, s, 0, false);
     const uint32_t far_blocks = p->far_nbx * p->far_nby * p->far_nbz;
     if (p->far_handled) {
         FarDescs fd;

@@ -538,12 +538,12 @@ ION_HD void combine_write(int tid, int nthreads, const Geom& g, uint32_t y, uint
 // Their field varies slowly over a few cells, so it is summed ONCE per FARB^3 block of cells as a second-order Taylor polynomial
 // about the block centre (value, gradient, Hessian of q f(r) and w x f(r), f = r/|r|^3) and every cell evaluates the polynomial:
 // the cost per cell no longer depends on the number of far sources.  Truncation error relative to the far field itself is
-// (|delta| / R)^3 with |delta| <= 2.6 cells; the host enables the path only when R >= 40 |delta| for every (cell, source) pair,
-// i.e. below 1.6e-5 of a contribution that is itself a fraction of the field (otherwise the direct kernel sums these sources).
+// (|delta| / R)^3 with |delta| <= 6.1 cells (FARB = 8); the host enables the path only when R >= 40 |delta| for every (cell, source)
+// pair, i.e. below 1.6e-5 of a contribution that is itself a fraction of the field (otherwise the direct kernel sums these sources).
 // Table layout: tens[FAR_T][nblocks], block index bx + nbx * (by + nby * bz); entries 0..29 = E part, 30..59 = B part, each
 // F0[3] | G[3][3] | H[3][6] with the pair order (xx, xy, xz, yy, yz, zz).
 // ------------------------------------------------------------------------------------------------------
-constexpr int FARB = 4;
+constexpr int FARB = 8;
 constexpr int FAR_T = 60;
 struct FarSource {
     float cx, cy, cz, q;

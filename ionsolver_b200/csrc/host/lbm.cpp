@@ -171,6 +171,9 @@ LbmDomain::~LbmDomain() {
 
 void LbmDomain::enqueue_initialize() { check(ion_enqueue_initialize(dev)); }
 void LbmDomain::enqueue_stream_collide() { check(ion_enqueue_stream_collide(dev, t, fx, fy, fz)); }
+void LbmDomain::enqueue_stream_collide_range(uint32_t z_begin, uint32_t z_end, bool finish) {
+    check(ion_enqueue_stream_collide_range(dev, t, fx, fy, fz, z_begin, z_end, finish ? 1 : 0));
+}
 void LbmDomain::enqueue_update_fields() { check(ion_enqueue_update_fields(dev, t, fx, fy, fz)); }
 void LbmDomain::enqueue_update_e_b_dyn() { check(ion_enqueue_update_e_b_dyn(dev)); }
 void LbmDomain::enqueue_lod_part_2_gather() { check(ion_enqueue_lod_part_2_gather(dev)); }
@@ -361,9 +364,47 @@ void Lbm::do_time_step() {  // mod.rs:250-272
     }
 }
 
+// z-slab decompositions (d_x = d_y = 1) with at least four layers per slab take the boundary-first schedule
+bool Lbm::boundary_first() const {
+    if (!overlap_halo || config.d_x != 1u || config.d_y != 1u || config.d_z < 2u) return false;
+    for (const auto& d : domains)
+        if (d.n_z < 4u) return false;
+    static const bool off = getenv("ION_NO_BOUNDARY_FIRST") && atoi(getenv("ION_NO_BOUNDARY_FIRST")) != 0;
+    return !off;
+}
+
 void Lbm::do_time_step_body() {
     const bool mhd = config.ext_magneto_hydro;
     if (mhd) clear_qu_lod();
+    if (boundary_first()) {
+        // Same operations as mod.rs:250-272, scheduled for overlap.  (1) stream_collide on the two layers next to the halos: they
+        // write every DDF the neighbours need (the extract kernels read layers 0/1 and nz-2/nz-1 only, sim_kernels.cl:1063-1069).
+        // (2) The halo stream of every domain is forked: extract -> exchange over NVLink -> insert of fi (and rho/u/flags, fqi, ei) run
+        // there.  (3) stream_collide on the interior layers runs meanwhile on the main stream -- insert only writes the halo cells'
+        // own slots of this step's parity, which no thread touches before the next step -- followed by the LOD exchange and
+        // update_e_b_dynamic, which never touch a DDF.  (4) join.
+        for (auto& d : domains) {
+            d.enqueue_stream_collide_range(1u, 2u, false);
+            d.enqueue_stream_collide_range(d.n_z - 2u, d.n_z - 1u, false);
+        }
+        for (auto& d : domains) check(ion_halo_fork(d.dev));
+        if (config.graphics_config.graphics_active) communicate_rho_u_flags();
+        communicate_fi();
+        if (mhd) {
+            communicate_fqi();
+            communicate_ei();
+        }
+        for (auto& d : domains) d.enqueue_stream_collide_range(2u, d.n_z - 2u, true);
+        if (mhd) {
+            build_lods_part_2();
+            communicate_qu_lods();
+            update_e_b_dynamic();
+        }
+        for (auto& d : domains) check(ion_halo_join(d.dev));
+        if (mhd && world == 1) finish_queues();  // see below: cross-stream LOD copies of a single process
+        increment_timestep(1);
+        return;
+    }
     stream_collide();
     if (config.graphics_config.graphics_active) communicate_rho_u_flags();
     if (mhd && get_d_n() > 1 && overlap_halo) {

@@ -155,6 +155,7 @@ struct LbmDomain {
 
     void enqueue_initialize();                 // domain.rs:412
     void enqueue_stream_collide();             // domain.rs:419
+    void enqueue_stream_collide_range(uint32_t z_begin, uint32_t z_end, bool finish);  // the same kernel on a range of z layers
     void enqueue_update_fields();              // domain.rs:432
     void enqueue_update_e_b_dyn();             // domain.rs:443
     void enqueue_lod_part_2_gather();          // domain.rs:453
@@ -201,6 +202,7 @@ struct Lbm {
     void run(uint64_t steps);     // mod.rs:235
     void do_time_step();          // mod.rs:250
     void do_time_step_body();
+    bool boundary_first() const;  // z slabs: boundary layers first, halo exchange overlapped with the interior update
     void finish_queues();         // mod.rs:275
     void precompute_B();          // mod.rs:284
     void precompute_E();          // mod.rs:301

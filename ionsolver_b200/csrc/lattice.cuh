@@ -48,6 +48,9 @@ struct KArgs {
     float ke, kmu, kmu0, kkge, kme, wq, kkbme, keabs;
     uint32_t lod_depth, n_lod, n_lod_own;
     float ecrf;
+    // stream_collide on a range of z layers (boundary-layer-first scheduling, ion_enqueue_stream_collide_range): the kernel's z is
+    // blockIdx.z + z_off and the launcher's grid is z_cnt layers high (0 = the whole domain)
+    uint32_t z_off, z_cnt;
 };
 
 __device__ __forceinline__ float sq(float x) { return x * x; }

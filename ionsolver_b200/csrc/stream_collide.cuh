@@ -115,7 +115,7 @@ template <int VS, int FP, bool MHD, bool TRT, bool ECR, bool ODD>
 __global__ void __launch_bounds__(ION_SC_BLOCK, ScMinBlocks<VS, FP, MHD, TRT>::value)
 k_stream_collide(const __grid_constant__ KArgs a, const float fx, const float fy, const float fz) {
     constexpr int QQ = VSet<VS>::Q;
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z + a.z_off;
     const bool inside = x < a.nx && !is_halo(a, x, y, z);  // sim.cl:485
     const Cell c = make_cell(a, inside ? x : 0u, y, z);
     const uint32_t n = c.n;
@@ -454,7 +454,9 @@ inline dim3 cell_grid(const KArgs& a, unsigned& block, unsigned cap = SC_BLOCK_M
 inline dim3 sc_grid(const KArgs& a, unsigned& block) {  // stream_collide: ION_SC_BLOCK threads, env ION_SC_BLOCK may lower it (A/B timing)
     static const unsigned env = getenv("ION_SC_BLOCK") ? (unsigned)atoi(getenv("ION_SC_BLOCK")) : 0u;
     const unsigned cap = (env >= 32u && env <= (unsigned)ION_SC_BLOCK) ? env : (unsigned)ION_SC_BLOCK;
-    return cell_grid(a, block, cap);
+    dim3 g = cell_grid(a, block, cap);
+    if (a.z_cnt) g.z = a.z_cnt;  // a range of z layers (KArgs::z_off, z_cnt)
+    return g;
 }
 
 // per-velocity-set launchers (one translation unit each, see sc_d*.cu)

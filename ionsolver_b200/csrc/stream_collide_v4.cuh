@@ -123,7 +123,7 @@ k_stream_collide_v4(const __grid_constant__ KArgs a, const float fx, const float
     constexpr int QQ = VSet<VS>::Q;
     typedef typename Codec<FP>::store_t S;
     const uint32_t nx = a.nx, ny = a.ny, nz = a.nz;
-    const uint32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u, y = blockIdx.y, z = blockIdx.z;
+    const uint32_t x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u, y = blockIdx.y, z = blockIdx.z + a.z_off;
     if (x0 >= nx) return;
     if (((a.dy > 1u) & (y == 0u || y >= ny - 1u)) || ((a.dz > 1u) & (z == 0u || z >= nz - 1u))) return;  // halo rows, sim.cl:145-148
     const uint64_t N = a.N;
@@ -229,7 +229,7 @@ inline bool launch_stream_collide_v4(const KArgs& a, int fp, bool trt, uint64_t 
     const unsigned threads_x = a.nx / 4u;
     unsigned block = ((threads_x + 31u) / 32u) * 32u;
     if (block > 64u) block = 64u;
-    const dim3 grid((threads_x + block - 1u) / block, a.ny, a.nz);
+    const dim3 grid((threads_x + block - 1u) / block, a.ny, a.z_cnt ? a.z_cnt : a.nz);
     const bool odd = (t & 1ull) != 0ull;
 #define ION_V4_CASE(FPV, TRTV)                                                                          \
     if (fp == FPV && trt == TRTV) {                                                                      \

@@ -117,9 +117,9 @@ def ragged_mhd_cases():
                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)),
         ("mhd_z3_d3q19_fp16s_lod4_ragged", _mhd(C(velocity_set="D3Q19", float_type="FP16S", n_x=16, n_y=32, n_z=48, d_z=3, nu=0.05,
                                                  ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 32.0, weak=True)),
-        # tall slabs (128 layers incl. halos): the third slab sees the first one 145+ cells away, far enough for the Taylor path of
-        # the far slabs (eb_fft.cu far_set); its neighbour's pyramid goes through the FFT as a second source set
-        ("mhd_z3_d3q19_fp32_lod4_tall", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=378, d_z=3, nu=0.05,
+        # tall slabs (256 layers incl. halos): the third slab sees the first one 289+ cells away, far enough for the Taylor path of
+        # the far slabs (eb_fft.cu far_set: R >= 40 x 6.06); its neighbour's pyramid goes through the FFT as a second source set
+        ("mhd_z3_d3q19_fp32_lod4_tall", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=762, d_z=3, nu=0.05,
                                               ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 16.0)),
     ]
 
