@@ -239,6 +239,12 @@ class ClockSampler:
         self.window = [None, None]  # perf_counter bounds of the timed region; the sampler itself starts before the warm-up
         self.thread = threading.Thread(target=self._run, daemon=True)
 
+    def wait_ready(self, timeout=3.0):
+        """Blocks until the sampler delivers (NVML initialisation takes ~100 ms): a timed region of a few milliseconds is still sampled."""
+        t0 = time.perf_counter()
+        while not self.samples and time.perf_counter() - t0 < timeout:
+            time.sleep(0.002)
+
     def begin(self):
         self.window[0] = time.perf_counter()
 
@@ -353,6 +359,8 @@ def build_scene(args, rank, world, device):
         for i, (f, ox, oy, kind, val) in enumerate(parts):
             lbm.import_mesh(os.path.join(REF_STL, f), 1.0, ox, oy, zc, 0.0, 0.0, 0.0)
             lbm.voxelise_mesh(i, kind, val)
+        for d in lbm.domains:  # 5.4 M magnet cells x 33.5 M outputs: the fast psi mode (rounding-level differences) keeps the scene build short
+            d.set_precompute_mode(1)
         lbm.precompute_B()
         lbm.precompute_E()
         for d in lbm.domains:
@@ -464,6 +472,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- whole-step throughput, inputs resident in HBM ----
     with ClockSampler(device) as clocks:  # started before the warm-up so that NVML is initialised when the timed region begins
+        clocks.wait_ready()
         for _ in range(max(args.warmup, 3)):
             lbm.do_time_step()
         barrier()
@@ -556,21 +565,24 @@ def run_ours(args, rank, world, local_rank):
         sections = [("flags", n, torch.uint8, 3), ("rho", n, torch.float32, 1), ("u", 3 * n, torch.float32, 2)]
         if mhd:
             sections.append(("q", n, torch.float32, 11))
-        host = {name: (torch.empty(sz, dtype=dt, pin_memory=True), fid) for name, sz, dt, fid in sections}
+        host = {name: (torch.empty(sz, dtype=dt, pin_memory=True), fid) for name, sz, dt, fid in sections}   # the state that is loaded
+        saved = {name: torch.empty(sz, dtype=dt, pin_memory=True) for name, sz, dt, fid in sections}           # where a state is saved to
         for name, (tns, fid) in host.items():
             tns.numpy()[:] = dom.read(fid)
         lib = capi.load()
-
-        def io(fn):
-            for name, (tns, fid) in host.items():
-                capi.check(fn(dom.handle, fid, ctypes.c_void_p(tns.data_ptr()), 0, tns.numel() * tns.element_size()))
+        k = len(sections)
+        c_fields = (ctypes.c_int * k)(*[fid for _, _, _, fid in sections])
+        c_out = (ctypes.c_void_p * k)(*[saved[name].data_ptr() for name, _, _, _ in sections])
+        c_in = (ctypes.c_void_p * k)(*[host[name][0].data_ptr() for name, _, _, _ in sections])
+        c_bytes = (ctypes.c_size_t * k)(*[host[name][0].numel() * host[name][0].element_size() for name, _, _, _ in sections])
 
         def e2e_step():
-            io(lib.ion_buffer_write)          # the .ion sections a loader uploads (file.rs:118-152), from pinned memory
+            # save the state the previous step left (file.rs:221-268) and load this step's (file.rs:118-152) from pinned host memory:
+            # one call, downloads and uploads overlapped on two streams
+            capi.check(lib.ion_buffer_swap(dom.handle, k, c_fields, c_out, c_in, c_bytes))
             lbm.initialize()                  # main.rs:274-278: a loaded state is re-initialised
             lbm.do_time_step()
             lbm.finish_queues()
-            io(lib.ion_buffer_read)           # the sections a writer downloads (file.rs:221-268)
 
         e2e_step()
         k_e2e = max(3, min(args.steps, 5))
@@ -587,8 +599,9 @@ def run_ours(args, rank, world, local_rank):
         nbytes = sum(t.numel() * t.element_size() for t, _ in host.values()) * world
         e2e = {"value": cells_global / dt / 1e6, "unit": "MLUPs/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                "ms_per_step": dt * 1e3, "host_link_gbs_aggregate": 2 * nbytes / dt / 1e9,
-               "what": "per step: upload flags/rho/u/Q from pinned host memory, Lbm::initialize, "
-               "Lbm::do_time_step, download flags/rho/u/Q (the load -> step -> save cycle of file.rs through the C ABI)"}
+               "what": "per step: ion_buffer_swap (download flags/rho/u/Q as the previous step left them, upload this step's from pinned host "
+                       "memory; the two directions overlap), Lbm::initialize, Lbm::do_time_step -- the save / load / step cycle of file.rs through the C ABI"}
+        del saved
         del host
     else:
         e2e = {"value": None, "unit": "MLUPs/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,

@@ -141,6 +141,9 @@ ION_API int ion_buffer_read(ion_domain_t* dom, int field, void* host, size_t off
 ION_API int ion_buffer_device_ptr(const ion_domain_t* dom, int field, void** dptr);
 /* device-to-device copy between two domains' buffers on dst's stream; the single-node replacement for the
  * host-staged std::ptr::swap exchange of mod.rs:380-384 and the LOD slice copy of mod.rs:460-462 */
+/* save-and-load: buffer fields[i] is read to host_out[i], then overwritten from host_in[i]; downloads and uploads overlap on two
+ * streams (file.rs:221-268 followed by :118-152 for the next state).  Pinned host memory; blocks until done. */
+ION_API int ion_buffer_swap(ion_domain_t* dom, int n, const int* fields, void* const* host_out, const void* const* host_in, const size_t* bytes);
 ION_API int ion_buffer_copy(ion_domain_t* dst, int dst_field, size_t dst_offset_bytes, ion_domain_t* src, int src_field,
                     size_t src_offset_bytes, size_t bytes);
 

@@ -41,7 +41,7 @@ SYMBOLS = [
     "ion_device_count", "ion_last_error_string", "ion_abi_version", "ion_domain_create", "ion_domain_destroy",
     "ion_domain_params", "ion_buffer_size", "ion_buffer_write", "ion_buffer_read", "ion_buffer_device_ptr",
     "ion_buffer_copy", "ion_enqueue_initialize", "ion_enqueue_stream_collide", "ion_enqueue_update_fields",
-    "ion_enqueue_stream_collide_range", "ion_enqueue_update_e_b_dyn", "ion_domain_eb_fft_info", "ion_domain_set_precompute_mode", "ion_enqueue_lod_part_2_gather", "ion_enqueue_clear_qu_lod",
+    "ion_enqueue_stream_collide_range", "ion_buffer_swap", "ion_enqueue_update_e_b_dyn", "ion_domain_eb_fft_info", "ion_domain_set_precompute_mode", "ion_enqueue_lod_part_2_gather", "ion_enqueue_clear_qu_lod",
     "ion_enqueue_transfer_extract", "ion_enqueue_transfer_insert", "ion_voxelize_mesh", "ion_enqueue_precompute_b",
     "ion_enqueue_precompute_e", "ion_enqueue_precompute_e_ecr", "ion_domain_set_ecr_freq", "ion_finish",
     "ion_kernel_launch_count", "ion_domain_stream",
@@ -136,6 +136,7 @@ def load() -> ctypes.CDLL:
     L.ion_enqueue_initialize.argtypes = [D]
     L.ion_enqueue_stream_collide.argtypes = [D, c.c_uint64, c.c_float, c.c_float, c.c_float]
     L.ion_enqueue_update_fields.argtypes = [D, c.c_uint64, c.c_float, c.c_float, c.c_float]
+    L.ion_buffer_swap.argtypes = [D, c.c_int, c.POINTER(c.c_int), c.POINTER(c.c_void_p), c.POINTER(c.c_void_p), c.POINTER(c.c_size_t)]
     L.ion_enqueue_stream_collide_range.argtypes = [D, c.c_uint64, c.c_float, c.c_float, c.c_float, c.c_uint32, c.c_uint32, c.c_int]
     L.ion_enqueue_update_e_b_dyn.argtypes = [D]
     L.ion_enqueue_lod_part_2_gather.argtypes = [D]

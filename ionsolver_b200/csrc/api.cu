@@ -408,6 +408,33 @@ int ion_buffer_read(ion_domain_t* d, int field, void* host, size_t off, size_t b
     ION_CUDA(cudaStreamSynchronize(d->stream));
     return ION_OK;
 }
+// Save-and-load in one call (file.rs:221-268 followed by :118-152 for the next state): every listed buffer is read to host_out[i]
+// and then overwritten from host_in[i].  The downloads run on the domain's stream and the uploads on its second stream, each
+// upload ordered behind the download of the same buffer only -- so host->device and device->host traffic overlap (PCIe is full
+// duplex) instead of running back to back.  Host memory should be pinned.  Blocks until both directions are done.
+int ion_buffer_swap(ion_domain_t* d, int n, const int* fields, void* const* host_out, const void* const* host_in, const size_t* bytes) {
+    if (!d || !fields || !host_out || !host_in || !bytes || n < 0) return fail(ION_ERR_INVALID, "NULL argument");
+    for (int i = 0; i < n; i++) {
+        int r = check_field(d, fields[i]);
+        if (r) return r;
+        if (bytes[i] > d->bytes[fields[i]]) return fail(ION_ERR_RANGE, "swap of %zu bytes exceeds buffer %d (%zu bytes)", bytes[i], fields[i], d->bytes[fields[i]]);
+        if ((!host_out[i] || !host_in[i]) && bytes[i]) return fail(ION_ERR_INVALID, "NULL host pointer");
+    }
+    if (d->halo_active) return fail(ION_ERR_INVALID, "ion_buffer_swap inside a halo fork");
+    ION_CUDA(cudaSetDevice(d->device));
+    ION_CUDA(cudaEventRecord(d->ev_fork, d->stream));  // the upload stream starts behind everything queued so far
+    ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev_fork, 0));
+    for (int i = 0; i < n; i++) {
+        ION_CUDA(cudaMemcpyAsync(host_out[i], d->buf[fields[i]], bytes[i], cudaMemcpyDeviceToHost, d->stream));
+        ION_CUDA(cudaEventRecord(d->ev, d->stream));
+        ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev, 0));
+        ION_CUDA(cudaMemcpyAsync(d->buf[fields[i]], host_in[i], bytes[i], cudaMemcpyHostToDevice, d->halo_stream));
+    }
+    ION_CUDA(cudaEventRecord(d->ev_join, d->halo_stream));
+    ION_CUDA(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
+    ION_CUDA(cudaStreamSynchronize(d->stream));
+    return ION_OK;
+}
 int ion_buffer_copy(ion_domain_t* dst, int df, size_t doff, ion_domain_t* src, int sf, size_t soff, size_t bytes) {
     int r = check_field(dst, df);
     if (r) return r;

@@ -46,6 +46,7 @@ struct EbFftPlan {
     int far_ndesc;
     FarSource* far_src;
     float* far_tens;         // [FAR_T][far_blocks]
+    uint32_t far_shift;      // log2 of the Taylor block edge: 3 (8^3) or 2 (4^3), chosen from the smallest source distance
     uint32_t far_nbx, far_nby, far_nbz;
 };
 
@@ -117,9 +118,9 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     float2* W = reinterpret_cast<float2*>(eb_smem);  // [2][P][6][M][ROW]
     float2* S0 = W + (size_t)2 * C::P * C::PLANE;     // s^_0 of the current planes [P][M][ROW] (single buffer, see below);
                                                       // NSETS = 2: the neighbour's compact spectrum [P][4][ND*ND] instead
-    float2* tw = S0 + (size_t)C::P * C::SLOT;
+    float4* tw = reinterpret_cast<float4*>(S0 + (size_t)C::P * C::SLOT);  // [H][ND/2], see main_phase_accumulate
     const int tid = threadIdx.x;
-    if (tid < C::M) tw[tid] = make_float2(tw_cos32(tid * (32 / C::M)), tw_sin32(tid * (32 / C::M)));
+    if (tid < C::H * (ND / 2)) tw[tid] = main_tw4<ND>(tid / (ND / 2), tid % (ND / 2));
     const Task t = tasks[blockIdx.x];
     const float2* kt = khat + (size_t)blockIdx.x * C::khat_per_task;
     const float2* kt2 = NSETS == 2 ? khat2 + (size_t)blockIdx.x * C::khat_per_task : nullptr;
@@ -200,7 +201,7 @@ __global__ void k_eb_far_sources(const __grid_constant__ FarDescs fd, const floa
 }
 // Taylor tensors of the far field, one thread per FARB^3 block of cells
 __global__ void __launch_bounds__(128) k_eb_far_tensors(const FarSource* __restrict__ src, const int nsrc, float* __restrict__ tens, const uint32_t nbx,
-                                                         const uint32_t nby, const uint32_t nbz) {
+                                                         const uint32_t nby, const uint32_t nbz, const uint32_t FARB) {
     __shared__ FarSource s_src[128];
     for (int k = threadIdx.x; k < nsrc; k += blockDim.x) s_src[k] = src[k];
     __syncthreads();
@@ -208,7 +209,7 @@ __global__ void __launch_bounds__(128) k_eb_far_tensors(const FarSource* __restr
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
     const uint32_t bx = b % nbx, by = (b / nbx) % nby, bz = b / (nbx * nby);
-    const float c = 0.5f * (float)(FARB - 1);
+    const float c = 0.5f * (float)(FARB - 1u);
     float t[FAR_T];
 #pragma unroll
     for (int i = 0; i < FAR_T; i++) t[i] = 0.0f;
@@ -226,7 +227,7 @@ template <int ND, int CH>
 __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom g, const float* __restrict__ scratch, const uint8_t* __restrict__ flags,
                                                      const float* __restrict__ E_stat, const float* __restrict__ B_stat, float* __restrict__ E_dyn,
                                                      float* __restrict__ B_dyn, const float* __restrict__ far_tens, const uint32_t far_nbx,
-                                                     const uint32_t far_blocks) {
+                                                     const uint32_t far_blocks, const uint32_t far_shift) {
     extern __shared__ __align__(128) unsigned char eb_smem[];
     float* tile = reinterpret_cast<float*>(eb_smem);  // [6][tile_len]
     const uint32_t y = blockIdx.x, z = blockIdx.y;
@@ -235,7 +236,8 @@ __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom
     const uint64_t base = ((uint64_t)y + (uint64_t)z * g.ny) * g.nx;
     // far slabs: the Taylor tensors of this row's FARB^3 blocks ([FAR_T][far_nbx] floats, after the six permuted rows)
     float* ftile = tile + (size_t)6 * tile_len;
-    const float fdy = (float)(y % FARB) - 0.5f * (float)(FARB - 1), fdz = (float)(z % FARB) - 0.5f * (float)(FARB - 1);
+    const uint32_t FARB = 1u << far_shift;
+    const float fdy = (float)(y % FARB) - 0.5f * (float)(FARB - 1u), fdz = (float)(z % FARB) - 0.5f * (float)(FARB - 1u);
     if (far_tens) {
         const uint32_t brow = (y / FARB + (g.ny + FARB - 1u) / FARB * (z / FARB)) * far_nbx;
         for (uint32_t i = threadIdx.x; i < (uint32_t)FAR_T * far_nbx; i += blockDim.x)
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom
                 float t[FAR_T];
 #pragma unroll
                 for (int i = 0; i < FAR_T; i++) t[i] = ftile[(size_t)i * far_nbx + x / FARB];
-                const float fdx = (float)(x % FARB) - 0.5f * (float)(FARB - 1);
+                const float fdx = (float)(x % FARB) - 0.5f * (float)(FARB - 1u);
 #pragma unroll
                 for (int c = 0; c < 3; c++) {
                     sum[c] += far_eval(t, c, fdx, fdy, fdz);
@@ -409,10 +411,11 @@ static void far_set(const KArgs& a, EbFftPlan* p) {
     p->far_n = 0;
     p->far_ndesc = 0;
     p->far_handled = false;
+    p->far_shift = 3u;
     if (p->foreign_domain < 0 || a.di < 2u) return;  // no far slab, or the neighbour is not on the FFT path either
     bool ok = a.nx <= 2048u && a.di - 1u <= 8u;
     uint32_t entry = a.n_lod_own;
-    const float dmax = 0.5f * (float)(FARB - 1) * 1.7320508f;
+    float r_min = 1.0e30f;
     for (uint32_t d = 0; d + 1u < a.di; d++) {
         const uint32_t ddz = a.di - d;
         const int level = (int)a.lod_depth - (int)ddz > 0 ? (int)a.lod_depth - (int)ddz : 0;
@@ -424,13 +427,17 @@ static void far_set(const KArgs& a, EbFftPlan* p) {
             f.bsx = (float)(a.nx / nf); f.bsy = (float)(a.ny / nf); f.bsz = (float)(a.nz / nf);
             f.shift_z = (float)(ddz * a.nz);
             const float top = ((float)(nf - 1u) * f.bsz + 0.5f * f.bsz) - f.shift_z;  // highest centre of this slab's level
-            if (1.0f - top < 40.0f * dmax) ok = false;                                // the lowest cell a slab updates is z = 1
+            r_min = fminf(r_min, 1.0f - top);                                          // the lowest cell a slab updates is z = 1
             p->far_n += (int)(nf * nf * nf);
         }
         entry += nf * nf * nf;
     }
-    if (p->far_n > 128) ok = false;
-    p->far_handled = ok && p->far_n > 0;
+    if (p->far_n > 128 || p->far_n == 0) ok = false;
+    const float d8 = 3.5f * 1.7320508f, d4 = 1.5f * 1.7320508f;  // largest offset from the centre of an 8^3 / 4^3 block
+    if (ok && r_min >= 40.0f * d8) p->far_shift = 3u;
+    else if (ok && r_min >= 25.0f * d4) p->far_shift = 2u;
+    else ok = false;
+    p->far_handled = ok;
     if (!p->far_handled) { p->far_n = 0; p->far_ndesc = 0; }
 }
 
@@ -466,7 +473,10 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
             if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)8 << 20) != cudaSuccess) cudaGetLastError();
         }
     }
-    p->far_nbx = (a.nx + FARB - 1u) / FARB; p->far_nby = (a.ny + FARB - 1u) / FARB; p->far_nbz = (a.nz + FARB - 1u) / FARB;
+    {
+        const uint32_t fb = 1u << p->far_shift;
+        p->far_nbx = (a.nx + fb - 1u) / fb; p->far_nby = (a.ny + fb - 1u) / fb; p->far_nbz = (a.nz + fb - 1u) / fb;
+    }
     cudaError_t e = cudaMalloc((void**)&p->tasks, tasks.size() * sizeof(Task));
     if (e == cudaSuccess && p->far_handled) e = cudaMalloc((void**)&p->far_src, 128 * sizeof(FarSource));
     if (e == cudaSuccess && p->far_handled) e = cudaMalloc((void**)&p->far_tens, (size_t)FAR_T * p->far_nbx * p->far_nby * p->far_nbz * sizeof(float));
@@ -523,7 +533,7 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
         fd.n = p->far_ndesc;
         for (int i = 0; i < fd.n; i++) fd.d[i] = p->far_desc[i];
         k_eb_far_sources<<<1, 128, 0, s>>>(fd, a.QU_lod, p->far_src);
-        k_eb_far_tensors<<<(far_blocks + 127u) / 128u, 128, 0, s>>>(p->far_src, p->far_n, p->far_tens, p->far_nbx, p->far_nby, p->far_nbz);
+        k_eb_far_tensors<<<(far_blocks + 127u) / 128u, 128, 0, s>>>(p->far_src, p->far_n, p->far_tens, p->far_nbx, p->far_nby, p->far_nbz, 1u << p->far_shift);
     }
     const float* far_tens = p->far_handled ? p->far_tens : nullptr;
     const uint32_t tile_len = (a.nx / ND) * (ND + 1) + ND + 1;
@@ -538,7 +548,7 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
             if (e != cudaSuccess) return e;                                                                                        \
         }                                                                                                                          \
         k_eb_combine<ND, CH><<<grid, threads, csmem, s>>>(p->g, p->scratch, a.flags, a.E_stat, a.B_stat, a.E_dyn, a.B_dyn, far_tens, \
-                                                          p->far_nbx, far_blocks);                                                  \
+                                                          p->far_nbx, far_blocks, p->far_shift);                                    \
     } while (0)
     if (chunks <= 1u) ION_COMBINE(1);
     else if (chunks <= 2u) ION_COMBINE(2);

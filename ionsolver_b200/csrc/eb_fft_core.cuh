@@ -81,8 +81,8 @@ template <int ND> struct Cfg {
     static constexpr int SLOT = M * ROW;        // float2 per (spectrum, kx) slot; K^ and s^ use the same padded rows in HBM
     static constexpr size_t khat_per_task = (size_t)3 * H * SLOT;  // float2
     static constexpr size_t shat_count = (size_t)4 * H * SLOT;     // float2
-    // work buffers [2][P][6 slots] + s^_0 staging [P slots] + x twiddles
-    static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + (size_t)P * SLOT * sizeof(float2) + M * sizeof(float2);
+    // work buffers [2][P][6 slots] + s^_0 staging [P slots] + x twiddle pairs [H][ND/2] float4
+    static constexpr size_t main_smem = (size_t)2 * P * PLANE * sizeof(float2) + (size_t)P * SLOT * sizeof(float2) + (size_t)H * (ND / 2) * sizeof(float4);
     // compact spectrum of a source set that lives on the ODD grid positions only (kind 1): s^(k + ND e_a) = -s^(k) on every axis, so
     // ND x ND values per (component, kx) describe the whole M x M plane
     static constexpr int CSLOT = ND * ND;
@@ -459,7 +459,8 @@ template <int ND> ION_HD void main_phase_y(int tid, int np, float2* W) {
     }
 }
 // phase 4: the x axis as a direct Hermitian DFT.  Thread = (y, z, x group); acc[6][XPT] stays in registers across the iterations.
-template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, const float2* W, const float2* tw, float (&acc)[6][Cfg<ND>::XPT]) {
+// tw4[kx][x/2] = (cos t(x), cos t(x+1), -sin t(x), -sin t(x+1)), t(x) = 2 pi kx x / M: two x outputs per packed FMA.
+template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, const float2* W, const float4* tw4, float (&acc)[6][Cfg<ND>::XPT]) {
     typedef Cfg<ND> C;
     constexpr int YZ = ND * ND;
     if (tid >= C::TACC) return;
@@ -470,14 +471,34 @@ template <int ND> ION_HD void main_phase_accumulate(int tid, int kx0, int np, co
         float2 v[6];
 #pragma unroll
         for (int s = 0; s < 6; s++) v[s] = W[((size_t)(p * 6 + s) * C::M + z) * C::ROW + y];
+        const float4* t4 = tw4 + (size_t)kx * (ND / 2) + xg * (C::XPT / 2);
 #pragma unroll
-        for (int i = 0; i < C::XPT; i++) {
-            const int x = xg * C::XPT + i;
-            const float2 cs = tw[(kx * x) & (C::M - 1)];
+        for (int i = 0; i < C::XPT; i += 2) {
+            const float4 cs = t4[i / 2];
+#if defined(__CUDA_ARCH__) && ION_FFT_PACKED
+            const float2 c2 = make_float2(cs.x, cs.y), s2 = make_float2(cs.z, cs.w);
 #pragma unroll
-            for (int s = 0; s < 6; s++) acc[s][i] = fmaf(v[s].x, cs.x, fmaf(-v[s].y, cs.y, acc[s][i]));
+            for (int s = 0; s < 6; s++) {
+                float2 a2 = make_float2(acc[s][i], acc[s][i + 1]);
+                a2 = __ffma2_rn(make_float2(v[s].x, v[s].x), c2, __ffma2_rn(make_float2(v[s].y, v[s].y), s2, a2));
+                acc[s][i] = a2.x;
+                acc[s][i + 1] = a2.y;
+            }
+#else
+#pragma unroll
+            for (int s = 0; s < 6; s++) {
+                acc[s][i] = fmaf(v[s].x, cs.x, fmaf(v[s].y, cs.z, acc[s][i]));
+                acc[s][i + 1] = fmaf(v[s].x, cs.y, fmaf(v[s].y, cs.w, acc[s][i + 1]));
+            }
+#endif
         }
     }
+}
+// the table of phase 4: entry (kx, j) for j < ND / 2
+template <int ND> ION_HD float4 main_tw4(int kx, int j) {
+    typedef Cfg<ND> C;
+    const int a0 = ((kx * (2 * j)) & (C::M - 1)) * (32 / C::M), a1 = ((kx * (2 * j + 1)) & (C::M - 1)) * (32 / C::M);
+    return make_float4(tw_cos32(a0), tw_cos32(a1), -tw_sin32(a0), -tw_sin32(a1));
 }
 // Hand-over of a task's sums.  The cells of one task are ds apart in x (one cell per 64 bytes at ds = 16), so writing E_dyn / B_dyn
 // -- and reading flags, E_stat, B_stat -- from here would touch one 32-byte sector per 4-byte access: 53 000 sector operations per
@@ -538,12 +559,12 @@ ION_HD void combine_write(int tid, int nthreads, const Geom& g, uint32_t y, uint
 // Their field varies slowly over a few cells, so it is summed ONCE per FARB^3 block of cells as a second-order Taylor polynomial
 // about the block centre (value, gradient, Hessian of q f(r) and w x f(r), f = r/|r|^3) and every cell evaluates the polynomial:
 // the cost per cell no longer depends on the number of far sources.  Truncation error relative to the far field itself is
-// (|delta| / R)^3 with |delta| <= 6.1 cells (FARB = 8); the host enables the path only when R >= 40 |delta| for every (cell, source)
-// pair, i.e. below 1.6e-5 of a contribution that is itself a fraction of the field (otherwise the direct kernel sums these sources).
+// (|delta| / R)^3, |delta| <= 6.1 cells for 8^3 blocks and 2.6 for 4^3.  The host picks the block size from the smallest
+// (cell, source) distance R: 8^3 when R >= 40 |delta| (error <= 1.6e-5 of the far field), 4^3 when R >= 25 |delta| (<= 6.4e-5 of a
+// contribution that is itself a fraction of the field); closer than that, the direct kernel sums these sources.
 // Table layout: tens[FAR_T][nblocks], block index bx + nbx * (by + nby * bz); entries 0..29 = E part, 30..59 = B part, each
 // F0[3] | G[3][3] | H[3][6] with the pair order (xx, xy, xz, yy, yz, zz).
 // ------------------------------------------------------------------------------------------------------
-constexpr int FARB = 8;
 constexpr int FAR_T = 60;
 struct FarSource {
     float cx, cy, cz, q;

@@ -121,6 +121,9 @@ def ragged_mhd_cases():
         # the far slabs (eb_fft.cu far_set: R >= 40 x 6.06); its neighbour's pyramid goes through the FFT as a second source set
         ("mhd_z3_d3q19_fp32_lod4_tall", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=762, d_z=3, nu=0.05,
                                               ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 16.0)),
+        # 128-layer slabs: the first slab is 145+ cells from the third, which selects the 4^3 Taylor blocks (R >= 25 x 2.6)
+        ("mhd_z3_d3q19_fp32_lod4_tall128", _mhd(C(velocity_set="D3Q19", float_type="FP32", n_x=16, n_y=16, n_z=378, d_z=3, nu=0.05,
+                                                 ext_volume_force=True, ext_magneto_hydro=True, mhd_lod_depth=4), 16.0)),
     ]
 
 

@@ -63,10 +63,11 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
     for (auto& v : Es) v = U(rng);
     for (auto& v : Bs) v = U(rng);
     flags[5 + 7 * nx + 9 * nx * ny] = 0x01;  // one solid cell: must stay untouched
-    std::vector<float2> W((size_t)C::P * C::PLANE), tw(C::M);
+    std::vector<float2> W((size_t)C::P * C::PLANE);
+    std::vector<float4> tw((size_t)C::H * (ND / 2));
     std::vector<float> scratch((size_t)6 * g.N, 0.0f);
     std::vector<float2> S0((size_t)C::P * C::SLOT);
-    for (int i = 0; i < C::M; i++) tw[i] = make_float2(tw_cos32(i * (32 / C::M)), tw_sin32(i * (32 / C::M)));
+    for (int i = 0; i < C::H * (ND / 2); i++) tw[i] = main_tw4<ND>(i / (ND / 2), i % (ND / 2));
     std::vector<float> accreg((size_t)C::T * 6 * C::XPT);
     std::vector<float2> khat2(nsets == 2 ? C::khat_per_task * ntasks : 0), shat2(nsets == 2 ? C::shat_count : 0);
     std::vector<float2> shat2c(nsets == 2 ? C::shatc_count : 0), S2c((size_t)C::P * 4 * C::CSLOT);
