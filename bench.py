@@ -485,30 +485,33 @@ def run_ours(args, rank, world, local_rank):
     value = cells_global / (ms_step * 1e-3) / 1e6
 
     # ---- per-kernel durations inside the step (CUDA events on the launching stream) ----
-    names = ["clear_qu_lod", "stream_collide", "update_e_b_dynamic"] if mhd else ["stream_collide"]
+    names = ["clear_qu_lod", "stream_collide", "lod_fold", "update_e_b_dynamic"] if mhd else ["stream_collide"]
     kern_ms = {k: 0.0 for k in names}
     k_prof = min(args.steps, 10)
     evs = []
     barrier()
     t = lbm.get_time_step()
     for s in range(k_prof):  # every rank times its own kernels (no collective inside these calls)
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
         e[0].record(stream)
         if mhd:
             dom.enqueue_clear_qu_lod()
         e[1].record(stream)
-        dom.enqueue_stream_collide(t + s)
+        dom.enqueue_stream_collide_range(t + s, 0, dom.n_z, False)   # the kernel alone ...
         e[2].record(stream)
+        dom.enqueue_stream_collide_range(t + s, 0, 0, True)           # ... and the fold of its LOD deposits (k_lod_fold)
+        e[3].record(stream)
         if mhd:
             dom.enqueue_update_e_b_dyn()
-        e[3].record(stream)
+        e[4].record(stream)
         evs.append(e)
     lbm.set_time_step(t + k_prof)
     barrier()
     for e in evs:
         if mhd:
             kern_ms["clear_qu_lod"] += e[0].elapsed_time(e[1]) / k_prof
-            kern_ms["update_e_b_dynamic"] += e[2].elapsed_time(e[3]) / k_prof
+            kern_ms["lod_fold"] += e[2].elapsed_time(e[3]) / k_prof
+            kern_ms["update_e_b_dynamic"] += e[3].elapsed_time(e[4]) / k_prof
         kern_ms["stream_collide"] += e[1].elapsed_time(e[2]) / k_prof
     if dist is not None:  # slabs differ in how many foreign LOD sources they sum over: report the slowest rank's kernels
         tk = torch.tensor([kern_ms[k] for k in sorted(kern_ms)], device=f"cuda:{device}", dtype=torch.float64)
@@ -547,6 +550,8 @@ def run_ours(args, rank, world, local_rank):
         eb["share_of_step"] = kern_ms["update_e_b_dynamic"] / ms_step
         kernels["update_e_b_dynamic"] = eb
         kernels["clear_qu_lod"] = {"ms": kern_ms["clear_qu_lod"], "share_of_step": kern_ms["clear_qu_lod"] / ms_step}
+        kernels["lod_fold"] = {"ms": kern_ms["lod_fold"], "share_of_step": kern_ms["lod_fold"] / ms_step,
+                               "what": "k_lod_fold: replicas of the finest LOD level -> QU_lod, launched by ion_enqueue_stream_collide after the kernel"}
     dom_name = max((k for k in kernels if "achieved" in kernels[k]), key=lambda k: kernels[k]["ms_per_launch"])
     roofline = {k: v for k, v in kernels[dom_name].items() if k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source",
                                                                      "algorithmic_bytes_per_launch", "ms_per_launch", "peak_source")}

@@ -308,6 +308,10 @@ class Domain:
     def enqueue_stream_collide(self, t, fx=0.0, fy=0.0, fz=0.0):
         check(self.lib.ion_enqueue_stream_collide(self.handle, t, fx, fy, fz))
 
+    def enqueue_stream_collide_range(self, t, z_begin, z_end, finish, fx=0.0, fy=0.0, fz=0.0):
+        """stream_collide on the z layers [z_begin, z_end); finish = last range of the step (folds the LOD deposits)."""
+        check(self.lib.ion_enqueue_stream_collide_range(self.handle, t, fx, fy, fz, z_begin, z_end, 1 if finish else 0))
+
     def enqueue_update_fields(self, t, fx=0.0, fy=0.0, fz=0.0):
         check(self.lib.ion_enqueue_update_fields(self.handle, t, fx, fy, fz))
 

@@ -84,6 +84,18 @@ __global__ void k_fill_f32(float* p, uint64_t n, float v) {
 
 using namespace ion;
 
+namespace {
+// frees device memory / destroys events on every exit path of the probe entry points (ION_CUDA returns early on errors)
+struct DevMem {
+    void* p = nullptr;
+    ~DevMem() { if (p) cudaFree(p); }
+};
+struct Event {
+    cudaEvent_t e = nullptr;
+    ~Event() { if (e) cudaEventDestroy(e); }
+};
+}  // namespace
+
 static thread_local char g_err[512] = "";
 namespace ion {
 std::atomic<uint64_t> g_launches{0};
@@ -126,9 +138,10 @@ int ion_codec_probe(int device, int float_type, int dir, const void* host_in, vo
     ION_CUDA(cudaSetDevice(device));
     const size_t ss = float_type == ION_FP32 ? 4 : 2;
     const size_t in_b = count * (dir == 0 ? 4 : ss), out_b = count * (dir == 0 ? ss : 4);
-    void *din = nullptr, *dout = nullptr;
-    ION_CUDA(cudaMalloc(&din, in_b ? in_b : 1));
-    ION_CUDA(cudaMalloc(&dout, out_b ? out_b : 1));
+    DevMem gin, gout;
+    ION_CUDA(cudaMalloc(&gin.p, in_b ? in_b : 1));
+    ION_CUDA(cudaMalloc(&gout.p, out_b ? out_b : 1));
+    void *din = gin.p, *dout = gout.p;
     ION_CUDA(cudaMemcpy(din, host_in, in_b, cudaMemcpyHostToDevice));
     const unsigned grid = (unsigned)((count + 255) / 256);
     if (count) {
@@ -138,8 +151,6 @@ int ion_codec_probe(int device, int float_type, int dir, const void* host_in, vo
         g_launches++;
     }
     cudaError_t e = cudaMemcpy(host_out, dout, out_b, cudaMemcpyDeviceToHost);
-    cudaFree(din);
-    cudaFree(dout);
     if (e != cudaSuccess) return cuda_fail(e, "codec probe");
     return ION_OK;
 }
@@ -150,11 +161,13 @@ int ion_measure_fma_peak(int device, int packed, double* fma_per_s) {
     int sms = 0;
     ION_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int blocks = sms * 8, threads = 256, iters = 4096;
-    float* out = nullptr;
-    ION_CUDA(cudaMalloc(&out, sizeof(float) * blocks * threads));
-    cudaEvent_t e0, e1;
-    ION_CUDA(cudaEventCreate(&e0));
-    ION_CUDA(cudaEventCreate(&e1));
+    DevMem gout;
+    ION_CUDA(cudaMalloc(&gout.p, sizeof(float) * blocks * threads));
+    float* out = (float*)gout.p;
+    Event g0, g1;
+    ION_CUDA(cudaEventCreate(&g0.e));
+    ION_CUDA(cudaEventCreate(&g1.e));
+    cudaEvent_t e0 = g0.e, e1 = g1.e;
     float best = 1e30f;
     for (int rep = 0; rep < 6; rep++) {
         cudaEventRecord(e0);
@@ -167,9 +180,6 @@ int ion_measure_fma_peak(int device, int packed, double* fma_per_s) {
         if (rep && ms < best) best = ms;
         g_launches++;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(out);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "fma peak probe");
     *fma_per_s = (double)blocks * threads * iters * 32.0 / (best * 1e-3);
@@ -444,13 +454,12 @@ int ion_buffer_copy(ion_domain_t* dst, int df, size_t doff, ion_domain_t* src, i
         return fail(ION_ERR_RANGE, "device copy out of range");
     ION_CUDA(cudaSetDevice(dst->device));
     if (src->stream != dst->stream) {  // order after everything already queued on the source domain
-        cudaEvent_t ev;
+        Event g;
         ION_CUDA(cudaSetDevice(src->device));
-        ION_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        ION_CUDA(cudaEventRecord(ev, src->stream));
+        ION_CUDA(cudaEventCreateWithFlags(&g.e, cudaEventDisableTiming));
+        ION_CUDA(cudaEventRecord(g.e, src->stream));
         ION_CUDA(cudaSetDevice(dst->device));
-        ION_CUDA(cudaStreamWaitEvent(dst->stream, ev, 0));
-        ION_CUDA(cudaEventDestroy(ev));
+        ION_CUDA(cudaStreamWaitEvent(dst->stream, g.e, 0));
     }
     if (src->device == dst->device)
         ION_CUDA(cudaMemcpyAsync((char*)dst->buf[df] + doff, (const char*)src->buf[sf] + soff, bytes, cudaMemcpyDeviceToDevice, dst->stream));
@@ -678,6 +687,11 @@ int ion_voxelize_mesh(ion_domain_t* d, const float* p0, const float* p1, const f
     float* dp = nullptr;  // p0|p1|p2 re-allocated per mesh like mesh.rs:282-287
     const size_t bytes = (size_t)triangles * 3 * sizeof(float);
     ION_CUDA(cudaMallocAsync((void**)&dp, 3 * bytes + 16, d->stream));
+    struct AsyncFree {  // the stream-ordered free also happens on the early returns below
+        float* p;
+        cudaStream_t s;
+        ~AsyncFree() { if (p) cudaFreeAsync(p, s); }
+    } guard{dp, d->stream};
     ION_CUDA(cudaMemcpyAsync(dp, p0, bytes, cudaMemcpyHostToDevice, d->stream));
     ION_CUDA(cudaMemcpyAsync(dp + 3 * (size_t)triangles, p1, bytes, cudaMemcpyHostToDevice, d->stream));
     ION_CUDA(cudaMemcpyAsync(dp + 6 * (size_t)triangles, p2, bytes, cudaMemcpyHostToDevice, d->stream));
@@ -685,7 +699,6 @@ int ion_voxelize_mesh(ion_domain_t* d, const float* p0, const float* p1, const f
     cudaError_t e = launch_voxelize(d->k, direction, flag, dp, dp + 3 * (size_t)triangles, dp + 6 * (size_t)triangles, triangles, bbu + 1,
                                     mx, my, mz, mhd, d->stream);
     g_launches++;
-    cudaFreeAsync(dp, d->stream);
     if (e != cudaSuccess) return cuda_fail(e, "voxelize_mesh launch");
     ION_CUDA(cudaStreamSynchronize(d->stream));  // host triangle arrays are borrowed only for the duration of the call
     return ION_OK;
