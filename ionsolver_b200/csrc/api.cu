@@ -603,16 +603,17 @@ int ion_enqueue_update_e_b_dyn(ion_domain_t* d) {
     ION_CUDA(cudaSetDevice(d->device));
     uint64_t l = 0;
     cudaError_t e;
-    // Default path: the own pyramid as a polyphase FFT convolution (eb_fft.cu) when the geometry allows it and the static
-    // kernel spectra (102 B per cell) fit in half of the free device memory (ION_EB_FFT=0 keeps the direct kernels,
-    // ION_EB_FFT_MAX_GB overrides the budget).  The deterministic mode always uses the reference-ordered direct kernel.
+    // Default path: the own pyramid as a polyphase FFT convolution (eb_fft.cu) when the geometry allows it.  Memory: 24 B per cell
+    // of scratch plus the static kernel spectra (102 B per cell) when both fit in three quarters of the free device memory, else the
+    // spectra are recomputed per batch of tasks every step (ION_EB_FFT=0 keeps the direct kernels, ION_EB_FFT_MAX_GB overrides the
+    // budget).  The deterministic mode always uses the reference-ordered direct kernel.
     if (!d->deterministic && !d->eb_plan_tried) {
         d->eb_plan_tried = true;
         const char* sw = getenv("ION_EB_FFT");
         if (!sw || atoi(sw) != 0) {
             size_t free_b = 0, total_b = 0;
             ION_CUDA(cudaMemGetInfo(&free_b, &total_b));
-            size_t budget = free_b / 2;
+            size_t budget = free_b / 4 * 3;  // what does not fit is streamed (recomputed per batch of tasks) or left to the direct kernels
             if (const char* gb = getenv("ION_EB_FFT_MAX_GB")) budget = (size_t)(atof(gb) * 1073741824.0);
             e = eb_fft_create(d->k, budget, d->stream, &d->eb_plan, &l);
             if (e != cudaSuccess) return cuda_fail(e, "update_e_b_dynamic: building the kernel spectra");

@@ -34,7 +34,11 @@ struct EbFftPlan {
     SourceSet sets[2];
     int foreign_domain;  // domain index whose pyramid is set 1, -1 = none (the direct kernel must then sum it)
     Task* tasks;
-    float2* khat;   // nsets * ntasks * khat_per_task
+    // Kernel spectra.  Static mode (batch == ntasks): all of them, computed once.  Streamed mode (they do not fit the memory budget,
+    // e.g. cfg5's 110 GB): a buffer for `batch` tasks per set, refilled by k_eb_khat in front of every k_eb_fft launch of a step
+    // -- the field update then costs one forward and one inverse transform per task instead of an inverse one, and no memory.
+    uint32_t batch;
+    float2* khat;   // nsets * batch * khat_per_task
     float2* shat;   // nsets * shat_count
     float2* shatc;  // compact spectrum of set 1 (odd-position symmetry), shatc_count
     float* scratch;  // the sums of a step before they are combined with the static fields: 6 floats per cell, rows permuted
@@ -51,7 +55,7 @@ struct EbFftPlan {
 };
 
 template <int ND>
-__global__ void __launch_bounds__(256) k_eb_khat(const __grid_constant__ Geom g, const __grid_constant__ SourceSet ss, const Task* __restrict__ tasks,
+__global__ void __launch_bounds__(Cfg<ND>::KT) k_eb_khat(const __grid_constant__ Geom g, const __grid_constant__ SourceSet ss, const Task* __restrict__ tasks,
                                                   float2* __restrict__ khat) {
     extern __shared__ __align__(128) unsigned char eb_smem[];
     float2* S = reinterpret_cast<float2*>(eb_smem);
@@ -320,8 +324,8 @@ bool eb_fft_supported(const KArgs& a) {
     // cells per axis at depth 3 and always at depth 4)
     const uint32_t sh = 1u << nd;
     if ((a.nx / sh > 1u) || (a.ny / sh > 1u) || (a.nz / sh > 1u)) return false;
-    const uint32_t dsz = a.nz / nd;
-    if (a.nz - nd * dsz >= dsz) return false;  // more than one extra z window cannot happen (nz < (nd+1)*dsz), but be explicit
+    // a slab with nz % nd layers beyond block nd-1 gets ONE extra z window (eb_fft_geometry): dsz = nz / nd >= 1 gives
+    // nz < nd * (dsz + 1) <= 2 * nd * dsz, so two windows always cover it
     return true;
 }
 
@@ -375,8 +379,9 @@ void eb_fft_destroy(EbFftPlan* p) {
 template <int ND> static cudaError_t build_khat(EbFftPlan* p, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
     if (e != cudaSuccess) return e;
+    if (p->batch < p->ntasks) return cudaSuccess;  // streamed mode: computed per batch inside every step
     for (int set = 0; set < p->nsets; set++)
-        k_eb_khat<ND><<<dim3(p->ntasks, 3), 256, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task);
+        k_eb_khat<ND><<<dim3(p->ntasks, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task);
     return cudaGetLastError();
 }
 
@@ -459,13 +464,19 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     const size_t per = p->nd == 16 ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
     const size_t sh = p->nd == 16 ? Cfg<16>::shat_count : Cfg<8>::shat_count;
     const size_t scratch_bytes = (size_t)6 * a.N * sizeof(float);
+    p->batch = p->ntasks;
     p->khat_bytes = (size_t)p->nsets * p->ntasks * per * sizeof(float2);
-    if (p->nsets == 2 && p->khat_bytes + scratch_bytes > budget_bytes) {  // no room for the neighbour's spectra: direct kernel for it
-        p->nsets = 1;
-        p->foreign_domain = -1;
-        p->khat_bytes = (size_t)p->ntasks * per * sizeof(float2);
+    const uint32_t forced = getenv("ION_EB_FFT_BATCH") ? (uint32_t)atoi(getenv("ION_EB_FFT_BATCH")) : 0u;  // test hook: streamed mode with this batch
+    if (p->khat_bytes + scratch_bytes > budget_bytes || (forced > 0u && forced < p->ntasks)) {
+        // streamed mode: spectra for `batch` tasks at a time (at most ~1.7 GB per set, at least a few waves of blocks)
+        const uint32_t min_batch = p->ntasks < 1024u ? p->ntasks : 1024u;
+        if (!forced && scratch_bytes + ((size_t)p->nsets * min_batch * per * sizeof(float2)) > budget_bytes) { delete p; return cudaSuccess; }
+        size_t room = forced ? forced : (budget_bytes - scratch_bytes) / ((size_t)p->nsets * per * sizeof(float2));
+        if (room > 2048u) room = 2048u;
+        p->batch = (uint32_t)room;
+        if (p->batch > p->ntasks) p->batch = p->ntasks;
+        p->khat_bytes = (size_t)p->nsets * p->batch * per * sizeof(float2);
     }
-    if (p->khat_bytes + scratch_bytes > budget_bytes) { delete p; return cudaSuccess; }
     far_set(a, p);
     {  // room for the pinned source spectra in L2 (a device-wide limit; a few MB of 126)
         size_t cur = 0;
@@ -518,14 +529,25 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     cudaError_t e = p->nsets == 2 ? cudaFuncSetAttribute(k_eb_fft<ND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem)
                                   : cudaFuncSetAttribute(k_eb_fft<ND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
     if (e != cudaSuccess) return e;
-    const size_t kstride = (size_t)p->ntasks * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
+    const size_t kstride = (size_t)p->batch * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
     for (int set = 0; set < p->nsets; set++)
         k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride, set == 1 ? p->shatc : nullptr);
+    const bool streamed = p->batch < p->ntasks;
+    if (streamed) {
+        e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
+        if (e != cudaSuccess) return e;
+    }
     pin_source_spectra(p, s, (size_t)p->nsets * sstride * sizeof(float2), true);
-    if (p->nsets == 2)
-        k_eb_fft<ND, 2><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, p->khat + kstride, p->shatc, p->scratch, 0);
-    else
-        k_eb_fft<ND, 1><<<p->ntasks, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
+    for (uint32_t t0 = 0; t0 < p->ntasks; t0 += p->batch) {
+        const uint32_t nt = p->ntasks - t0 < p->batch ? p->ntasks - t0 : p->batch;
+        if (streamed)
+            for (int set = 0; set < p->nsets; set++)
+                k_eb_khat<ND><<<dim3(nt, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks + t0, p->khat + (size_t)set * kstride);
+        if (p->nsets == 2)
+            k_eb_fft<ND, 2><<<nt, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks + t0, p->khat, p->shat, p->khat + kstride, p->shatc, p->scratch, 0);
+        else
+            k_eb_fft<ND, 1><<<nt, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks + t0, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
+    }
     pin_source_spectra(p, s, 0, false);
     const uint32_t far_blocks = p->far_nbx * p->far_nby * p->far_nbz;
     if (p->far_handled) {
@@ -559,7 +581,8 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    *launches += 2u + (uint64_t)p->nsets + (p->far_handled ? 2u : 0u);
+    const uint64_t batches = (p->ntasks + p->batch - 1u) / p->batch;
+    *launches += 1u + (uint64_t)p->nsets + batches * (p->batch < p->ntasks ? 1u + (uint64_t)p->nsets : 1u) + (p->far_handled ? 2u : 0u);
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }
@@ -567,5 +590,6 @@ int eb_fft_plan_foreign_domain(const EbFftPlan* p) { return p ? p->foreign_domai
 bool eb_fft_plan_far_handled(const EbFftPlan* p) { return p && p->far_handled; }
 size_t eb_fft_scratch_bytes(const EbFftPlan* p) { return p ? (size_t)6 * p->g.N * sizeof(float) : 0; }
 uint32_t eb_fft_plan_tasks(const EbFftPlan* p) { return p ? p->ntasks : 0; }
+uint32_t eb_fft_plan_batch(const EbFftPlan* p) { return p ? p->batch : 0; }
 
 }  // namespace ion

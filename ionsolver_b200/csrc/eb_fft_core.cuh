@@ -88,6 +88,7 @@ template <int ND> struct Cfg {
     static constexpr int CSLOT = ND * ND;
     static constexpr size_t shatc_count = (size_t)4 * H * CSLOT;
     static constexpr size_t khat_smem = (size_t)H * M * ROW * sizeof(float2);
+    static constexpr int KT = ((H * M + 31) / 32) * 32;  // threads of k_eb_khat: one (kx, line) FFT each in its y and z passes (544 / 160)
     static constexpr size_t src_smem = (size_t)M * ROW * sizeof(float2);
 };
 
@@ -195,31 +196,41 @@ ION_HD float2 cmul_sub(float2 a, float2 b, float2 c, float2 d) {
 // signed block difference of circular index m
 template <int ND> ION_HD int circ_diff(int m) { return m < ND ? m : m - 2 * ND; }
 
+template <int ND> ION_HD float khat_value(const Geom& g, const SourceSet& ss, const Task t, int comp, int ddx, int ddy, int ddz, float ry, float rz) {
+    // r = (float)cell - ((float)c * ds + 0.5 ds): integers and half-integers below 2^12, exact in FP32 (sim.cl:945, :440-447);
+    // r^2 < 2^24 is exact too up to 1024-cell blocks.  1 / (r^2 sqrt(r^2)) in IEEE FP32 (three roundings, <= 1.5 ulp): below the
+    // 2e-7 the FP32 transforms carry, and several times cheaper than FP64 -- it matters in streamed mode, where K^ is rebuilt every step
+    const float rx = (float)ddx * (float)g.dsx + ((float)t.ox + ss.offx);
+    const float r2 = rx * rx + (ry * ry + rz * rz);
+    if ((ss.kind == 0u && ddx == 0 && ddy == 0 && ddz == 0) || !(r2 > 0.0f)) return 0.0f;  // the cell's own block contributes nothing (sim.cl:944)
+    const float inv = 1.0f / (r2 * sqrtf(r2));
+    return (comp == 0 ? rx : comp == 1 ? ry : rz) * inv;
+}
+// x transform of the real kernel, two y lines per complex FFT: z = K(my) + i K(my+1), K^(my)[k] = (z[k] + conj z[M-k]) / 2,
+// K^(my+1)[k] = -i (z[k] - conj z[M-k]) / 2; the factor 1/2 is applied with the normalisation in khat_phase_z (a power of two: exact)
 template <int ND> ION_HD void khat_phase_x(int tid, int nthreads, const Geom& g, const SourceSet& ss, const Task t, int comp, float2* S) {
     typedef Cfg<ND> C;
-    for (int line = tid; line < C::M * C::M; line += nthreads) {
-        const int mz = line / C::M, my = line % C::M;
-        const int ddy = circ_diff<ND>(my);
+    for (int pair = tid; pair < C::M * C::M / 2; pair += nthreads) {
+        const int mz = pair / (C::M / 2), my = 2 * (pair % (C::M / 2));
+        const int ddy0 = circ_diff<ND>(my), ddy1 = circ_diff<ND>(my + 1);
         const int ddz = circ_diff<ND>(mz) + ND * (int)t.wz + ss.zadd;  // true block difference along z
-        // r = (float)cell - ((float)c * ds + 0.5 ds): small integers and half-integers, exact in any precision (sim.cl:945, :440-447)
-        const double ry = (double)ddy * g.dsy + ((double)t.oy + (double)ss.offy);
-        const double rz = (double)ddz * g.dsz + ((double)t.oz + (double)ss.offz);
+        const float ry0 = (float)ddy0 * (float)g.dsy + ((float)t.oy + ss.offy);
+        const float ry1 = (float)ddy1 * (float)g.dsy + ((float)t.oy + ss.offy);
+        const float rz = (float)ddz * (float)g.dsz + ((float)t.oz + ss.offz);
         float2 a[C::M];
 #pragma unroll
         for (int mx = 0; mx < C::M; mx++) {
             const int ddx = circ_diff<ND>(mx);
-            const double rx = (double)ddx * g.dsx + ((double)t.ox + (double)ss.offx);
-            const double r2 = rx * rx + ry * ry + rz * rz;
-            double k = 0.0;
-            if (!(ss.kind == 0u && ddx == 0 && ddy == 0 && ddz == 0) && r2 > 0.0) {  // the cell's own block contributes nothing (sim.cl:944)
-                const double inv = 1.0 / (r2 * sqrt(r2));
-                k = (comp == 0 ? rx : comp == 1 ? ry : rz) * inv;
-            }
-            a[mx] = make_float2((float)k, 0.0f);
+            a[mx] = make_float2(khat_value<ND>(g, ss, t, comp, ddx, ddy0, ddz, ry0, rz), khat_value<ND>(g, ss, t, comp, ddx, ddy1, ddz, ry1, rz));
         }
         fft_reg<C::M, false>(a);
+        float2* row = S + (size_t)mz * C::ROW + my;
 #pragma unroll
-        for (int kx = 0; kx < C::H; kx++) S[(kx * C::M + mz) * C::ROW + my] = a[kx];
+        for (int kx = 0; kx < C::H; kx++) {
+            const float2 z = a[kx], m = a[(C::M - kx) % C::M];
+            row[(size_t)kx * C::M * C::ROW] = make_float2(z.x + m.x, z.y - m.y);
+            row[(size_t)kx * C::M * C::ROW + 1] = make_float2(z.y + m.y, m.x - z.x);
+        }
     }
 }
 template <int ND> ION_HD void khat_phase_y(int tid, int nthreads, float2* S) {
@@ -245,7 +256,7 @@ template <int ND> ION_HD void khat_phase_z(int tid, int nthreads, int task, int 
         for (int i = 0; i < C::M; i++) a[i] = S[(kx * C::M + i) * C::ROW + ky];
         fft_reg<C::M, false>(a);
         // 1 / M^3 of the inverse transform; planes 1..ND-1 stand for themselves and their conjugates (Hermitian fold)
-        const float scale = (kx == 0 || kx == ND ? 1.0f : 2.0f) / (float)(C::M * C::M * C::M);
+        const float scale = (kx == 0 || kx == ND ? 0.5f : 1.0f) / (float)(C::M * C::M * C::M);  // incl. the 1/2 of khat_phase_x
         float2* out = khat + ((size_t)task * 3 + comp) * C::H * C::SLOT + (size_t)kx * C::SLOT + ky;
 #pragma unroll
         for (int kz = 0; kz < C::M; kz++) out[(size_t)kz * C::ROW] = make_float2(a[kz].x * scale, a[kz].y * scale);
