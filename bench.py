@@ -89,6 +89,33 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def bind_to_gpu_numa_node(device):
+    """Pin this rank's thread (and with it the pages of every pinned staging buffer it allocates afterwards: first touch) to the
+    CPUs of the NUMA node its GPU hangs off -- host <-> device copies of eight ranks otherwise cross the socket interconnect at
+    random.  Returns (description for the JSON line, the previous affinity mask or None)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return {"numa_node": None, "bound": False, "why": "the platform reports no NUMA node for the GPU"}, None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        before = os.sched_getaffinity(0)
+        allowed = before & cpus
+        if not allowed:
+            return {"numa_node": node, "bound": False, "why": "none of the node's CPUs is in this process's cpuset"}, None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "bound": True, "cpus": len(allowed), "cpus_before": len(before)}, before
+    except Exception as e:  # a sandbox without sysfs: leave the scheduler alone
+        return {"numa_node": None, "bound": False, "why": f"{type(e).__name__}: {e}"}, None
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own kernels on host cores, on a bounded sample of the workload
 # ----------------------------------------------------------------------------------------------------------------
@@ -359,8 +386,8 @@ def build_scene(args, rank, world, device):
         for i, (f, ox, oy, kind, val) in enumerate(parts):
             lbm.import_mesh(os.path.join(REF_STL, f), 1.0, ox, oy, zc, 0.0, 0.0, 0.0)
             lbm.voxelise_mesh(i, kind, val)
-        for d in lbm.domains:  # 5.4 M magnet cells x 33.5 M outputs: the fast psi mode (rounding-level differences) keeps the scene build short
-            d.set_precompute_mode(1)
+        for d in lbm.domains:  # 5.4 M magnet cells x 33.5 M outputs = 100 s (fast direct sum) or 163 s (reference order): FFT convolution, 0.4 s
+            d.set_precompute_mode(args.precompute_mode if args.precompute_mode >= 0 else 2)
         lbm.precompute_B()
         lbm.precompute_E()
         for d in lbm.domains:
@@ -376,7 +403,12 @@ def build_scene(args, rank, world, device):
         n = cfg["n"][0]
         lbm.import_mesh_reposition(os.path.join(REF_STL, "disk-magnet.stl"), 0.5 * n + 0.1, 0.5 * n + 0.1, 0.5 * g[2], 0.0, 0.0, 0.0, 0.5 * n - 1.0)
         lbm.voxelise_mesh(0, L.ModelType.Magnet, (0.0, 1000000.0, 0.0))
+        if args.precompute_mode >= 0:
+            for d in lbm.domains:
+                d.set_precompute_mode(args.precompute_mode)
+        t_pre = time.perf_counter()
         lbm.precompute_B()
+        print(f"precompute_B (mode {max(args.precompute_mode, 0)}): {time.perf_counter() - t_pre:.3f} s", file=sys.stderr)
     else:
         for d in lbm.domains:  # uniform B_stat = (0, 0, 0.01) LU written like a scene would (setup.rs:182-190)
             b = np.zeros(3 * d.n, np.float32)
@@ -437,6 +469,7 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     device = local_rank
     torch.cuda.set_device(device)
+    numa, affinity_before = bind_to_gpu_numa_node(device)
     t_build = time.perf_counter()
     lbm = build_scene(args, rank, world, device)
     lbm.finish_queues()
@@ -603,7 +636,7 @@ def run_ours(args, rank, world, local_rank):
             dt = float(tt.item())
         nbytes = sum(t.numel() * t.element_size() for t, _ in host.values()) * world
         e2e = {"value": cells_global / dt / 1e6, "unit": "MLUPs/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-               "ms_per_step": dt * 1e3, "host_link_gbs_aggregate": 2 * nbytes / dt / 1e9,
+               "ms_per_step": dt * 1e3, "host_link_gbs_aggregate": 2 * nbytes / dt / 1e9, "numa": numa,
                "what": "per step: ion_buffer_swap (download flags/rho/u/Q as the previous step left them, upload this step's from pinned host "
                        "memory; the two directions overlap), Lbm::initialize, Lbm::do_time_step -- the save / load / step cycle of file.rs through the C ABI"}
         del saved
@@ -613,6 +646,8 @@ def run_ours(args, rank, world, local_rank):
                "what": f"skipped: {host_bytes / 1e9:.0f} GB of pinned host staging per rank"}
 
     cpu, parity = None, None
+    if affinity_before is not None:
+        os.sched_setaffinity(0, affinity_before)  # the CPU arm uses every core this process may run on
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_reference_run(cfg, 2, 1, args.lod_depth, keep_state=True)
         cpu = {"value": r["mlups"], "unit": "MLUPs/s", "cores": r["cores"], "kind": r["kind"], "ms_per_step": r["ms"],
@@ -647,6 +682,8 @@ def main():
     ap.add_argument("--lod-depth", type=int, default=4, help="mhd_lod_depth (reference default 4, mod.rs:126)")
     ap.add_argument("--cells-z", type=int, default=0, help="override the z extent of the configuration's lattice (memory-limited boxes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precompute-mode", type=int, default=-1, choices=[-1, 0, 1, 2],
+                    help="static-field precompute of the scene build: 0 reference order, 1 fast direct sum, 2 FFT convolution (default: 0, cfg3: 2)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -163,7 +163,9 @@ ION_API int ion_enqueue_stream_collide_range(ion_domain_t* dom, uint64_t t, floa
 ION_API int ion_enqueue_update_fields(ion_domain_t* dom, uint64_t t, float fx, float fy, float fz);  /* domain.rs:432-441 */
 ION_API int ion_enqueue_update_e_b_dyn(ion_domain_t* dom);                                      /* domain.rs:443-451 */
 /* no reference counterpart: 0 (default) = psi_from_mesh with the reference's arithmetic and summation order (B_stat bit-identical to the
- * reference build), 1 = the same sum with rsqrt / fused multiply-adds, four outputs per thread (~5x faster, psi within ~1e-6 relative L2) */
+ * reference build), 1 = the same sum with rsqrt / fused multiply-adds, four outputs per thread (~5x faster, psi within ~1e-6 relative L2),
+ * 2 = psi_from_mesh and static_e_from_mesh as zero-padded FFT convolutions of the source cells with d/|d|^3 (cuFFT transforms, loaded at
+ * run time; O(P^3 log P) instead of O(cells x sources); psi / E_stat within ~1e-5 relative L2; ION_ERR_ABSENT when cuFFT or memory is missing) */
 ION_API int ion_domain_set_precompute_mode(ion_domain_t* dom, int mode);
 /* no reference counterpart: size of the static kernel spectra of the polyphase-FFT field update (0 = direct kernels in use)
  * and the number of polyphase problems per step; valid after the first ion_enqueue_update_e_b_dyn */

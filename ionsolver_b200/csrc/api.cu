@@ -41,6 +41,8 @@ size_t compaction_scratch_bytes(uint64_t N);
 cudaError_t count_sources(const KArgs& a, uint8_t mask, uint32_t* counts, uint32_t* host_total, cudaStream_t s);
 size_t field_source_bytes(uint32_t count);
 cudaError_t launch_precompute_b(const KArgs& a, uint32_t* counts, void* table, cudaStream_t s, int fast);
+cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t* counts, void* table, uint32_t total, cudaStream_t s, uint64_t* launches,
+                                  const char** why);
 cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void* table, cudaStream_t s);
 
 // FP32 issue-peak probe for bench.py's compute roofline (MEASURED_PEAKS.json only carries HBM and BF16 numbers):
@@ -420,7 +422,7 @@ int ion_buffer_read(ion_domain_t* d, int field, void* host, size_t off, size_t b
 }
 // Save-and-load in one call (file.rs:221-268 followed by :118-152 for the next state): every listed buffer is read to host_out[i]
 // and then overwritten from host_in[i].  The downloads run on the domain's stream and the uploads on its second stream, each
-// upload ordered behind the download of the same buffer only -- so host->device and device->host traffic overlap (PCIe is full
+// upload ordered behind the download of the same bytes only -- so host->device and device->host traffic overlap (PCIe is full
 // duplex) instead of running back to back.  Host memory should be pinned.  Blocks until both directions are done.
 int ion_buffer_swap(ion_domain_t* d, int n, const int* fields, void* const* host_out, const void* const* host_in, const size_t* bytes) {
     if (!d || !fields || !host_out || !host_in || !bytes || n < 0) return fail(ION_ERR_INVALID, "NULL argument");
@@ -434,11 +436,18 @@ int ion_buffer_swap(ion_domain_t* d, int n, const int* fields, void* const* host
     ION_CUDA(cudaSetDevice(d->device));
     ION_CUDA(cudaEventRecord(d->ev_fork, d->stream));  // the upload stream starts behind everything queued so far
     ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev_fork, 0));
+    // in chunks: the upload of a chunk waits for the download of the same chunk only, so the upload direction lags the download
+    // direction by 8 MiB instead of by a whole buffer (a wait refers to the event's latest record at the time of the call, so one
+    // event serves every chunk)
+    const size_t chunk = (size_t)8 << 20;
     for (int i = 0; i < n; i++) {
-        ION_CUDA(cudaMemcpyAsync(host_out[i], d->buf[fields[i]], bytes[i], cudaMemcpyDeviceToHost, d->stream));
-        ION_CUDA(cudaEventRecord(d->ev, d->stream));
-        ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev, 0));
-        ION_CUDA(cudaMemcpyAsync(d->buf[fields[i]], host_in[i], bytes[i], cudaMemcpyHostToDevice, d->halo_stream));
+        for (size_t off = 0; off < bytes[i]; off += chunk) {
+            const size_t len = bytes[i] - off < chunk ? bytes[i] - off : chunk;
+            ION_CUDA(cudaMemcpyAsync((char*)host_out[i] + off, (const char*)d->buf[fields[i]] + off, len, cudaMemcpyDeviceToHost, d->stream));
+            ION_CUDA(cudaEventRecord(d->ev, d->stream));
+            ION_CUDA(cudaStreamWaitEvent(d->halo_stream, d->ev, 0));
+            ION_CUDA(cudaMemcpyAsync((char*)d->buf[fields[i]] + off, (const char*)host_in[i] + off, len, cudaMemcpyHostToDevice, d->halo_stream));
+        }
     }
     ION_CUDA(cudaEventRecord(d->ev_join, d->halo_stream));
     ION_CUDA(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
@@ -716,8 +725,20 @@ static int precompute(ion_domain_t* d, int which) {
     if (e != cudaSuccess) return cuda_fail(e, "source count");
     void* table = nullptr;
     ION_CUDA(cudaMallocAsync(&table, field_source_bytes(total), d->stream));
+    if (d->precompute_mode == 2 && total > 0u) {  // FFT convolution (cuFFT transforms); an empty source set takes the direct kernels
+        float* E = which == 0 ? nullptr : which == 1 ? d->k.E_stat : (float*)d->buf[ION_FIELD_E_VAR];
+        if (which != 0 && !E) { cudaFreeAsync(table, d->stream); return fail(ION_ERR_ABSENT, "E_var needs ext_subgrid_ecr (domain.rs:573)"); }
+        const char* why = nullptr;
+        uint64_t l = 0;
+        e = launch_precompute_fft(d->k, which, E, d->cp_counts, table, total, d->stream, &l, &why);
+        g_launches += l;
+        cudaFreeAsync(table, d->stream);
+        if (e == cudaErrorNotSupported && why) return fail(ION_ERR_ABSENT, "FFT precompute mode: %s", why);
+        if (e != cudaSuccess) return cuda_fail(e, "static field precompute (FFT mode)");
+        return ION_OK;
+    }
     if (which == 0) {
-        e = launch_precompute_b(d->k, d->cp_counts, table, d->stream, d->precompute_fast ? 1 : 0);
+        e = launch_precompute_b(d->k, d->cp_counts, table, d->stream, d->precompute_mode == 1 ? 1 : 0);
         g_launches += 5;
     } else {
         float* E = which == 1 ? d->k.E_stat : (float*)d->buf[ION_FIELD_E_VAR];
@@ -735,8 +756,8 @@ int ion_enqueue_precompute_e_ecr(ion_domain_t* d) { return precompute(d, 2); }
 
 int ion_domain_set_precompute_mode(ion_domain_t* d, int mode) {
     if (!d) return fail(ION_ERR_INVALID, "NULL domain");
-    if (mode < 0 || mode > 1) return fail(ION_ERR_INVALID, "precompute mode %d (0 = reference arithmetic and order, 1 = fast)", mode);
-    d->precompute_fast = mode == 1;
+    if (mode < 0 || mode > 2) return fail(ION_ERR_INVALID, "precompute mode %d (0 = reference arithmetic and order, 1 = fast direct sum, 2 = FFT convolution)", mode);
+    d->precompute_mode = mode;
     return ION_OK;
 }
 

@@ -31,7 +31,7 @@ struct ion_domain {
     bool deterministic;   // ION_EXT_DETERMINISTIC: reference-ordered LOD sums and reference arithmetic in update_e_b_dynamic
     ion::EbFftPlan* eb_plan;  // polyphase-FFT update_e_b_dynamic (eb_fft.cu): static kernel spectra, built on first use
     bool eb_plan_tried;
-    bool precompute_fast;     // ion_domain_set_precompute_mode: rsqrt / FMA form of psi_from_mesh (rounding-level differences)
+    int precompute_mode;      // ion_domain_set_precompute_mode: 0 reference order, 1 rsqrt / FMA direct sum, 2 FFT convolution
 };
 
 #ifndef ION_LOD_REPLICAS

@@ -10,6 +10,12 @@
 // the order, so a deterministic two-pass count/scan/scatter is used); the field kernels then stream that table
 // through shared memory.  Because the order of the float sums (ascending source index) and every arithmetic
 // operation (IEEE sqrt/div, no contraction) equal the reference's, psi/B_stat/E_stat come out bit-identical.
+#include <cufft.h>
+#include <dlfcn.h>
+
+#include <climits>
+#include <cstring>
+
 #include "lattice.cuh"
 
 namespace ion {
@@ -411,6 +417,219 @@ cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void
     if (b > (unsigned)SF_BLOCK) b = SF_BLOCK;
     k_static_e<<<dim3((a.nx + b - 1u) / b, a.ny, a.nz), b, 0, s>>>(a, E, src, counts + nblocks);
     return cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Mode 2 of the static-field precompute (opt-in, ion_domain_set_precompute_mode): the sums of psi_from_mesh (sim.cl:1234-1251) and
+// static_e_from_mesh (sim.cl:1278-1300) are convolutions of the source cells with G(d) = d / |d|^3 on the cell lattice,
+//     psi(x) = 1/(4 pi) sum_s M_s . G(x - c_s),        E(x) = ke sum_s q_s G(x - c_s),
+// so they cost O(P^3 log P) through a zero-padded 3-D FFT instead of O(cells x sources): cfg3's 5.4 M magnet cells x 34 M outputs are
+// 1.8e14 pair terms for the direct kernels.  P_a = (outputs + extent of the sources' bounding box - 1) per axis, rounded up to a
+// 7-smooth length: with K[j mod P] = G(j - min) for j in [-(S-1), L-1] the circular convolution of the box-relative sources with K
+// has no wrap-around on the L outputs.  The transforms are plain library FFTs (cuFFT R2C / C2R, bound at run time so that the library
+// loads without it) off the time-step path; source scatter, kernel sampling, spectral products and the write-back are kernels here.
+// Same sum in a different order and FP32 transforms: ~1e-6 of the largest |psi| everywhere -- relative to the LOCAL field that is more
+// than the direct modes' rounding far away from the sources, which is why the mode is opt-in and has its own tolerance test.
+// ------------------------------------------------------------------------------------------------------------------------------
+struct CufftApi {
+    bool ok;
+    cufftResult (*Plan3d)(cufftHandle*, int, int, int, cufftType);
+    cufftResult (*SetStream)(cufftHandle, cudaStream_t);
+    cufftResult (*ExecR2C)(cufftHandle, cufftReal*, cufftComplex*);
+    cufftResult (*ExecC2R)(cufftHandle, cufftComplex*, cufftReal*);
+    cufftResult (*Destroy)(cufftHandle);
+};
+static const CufftApi& cufft_api() {
+    static const CufftApi api = [] {
+        CufftApi a;
+        memset(&a, 0, sizeof(a));
+        const char* names[] = {"libcufft.so.11", "libcufft.so", "/usr/local/cuda/lib64/libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so"};
+        void* h = nullptr;
+        for (const char* n : names)
+            if ((h = dlopen(n, RTLD_NOW | RTLD_LOCAL)) != nullptr) break;
+        if (!h) return a;
+        *(void**)(&a.Plan3d) = dlsym(h, "cufftPlan3d");
+        *(void**)(&a.SetStream) = dlsym(h, "cufftSetStream");
+        *(void**)(&a.ExecR2C) = dlsym(h, "cufftExecR2C");
+        *(void**)(&a.ExecC2R) = dlsym(h, "cufftExecC2R");
+        *(void**)(&a.Destroy) = dlsym(h, "cufftDestroy");
+        a.ok = a.Plan3d && a.SetStream && a.ExecR2C && a.ExecC2R && a.Destroy;
+        return a;
+    }();
+    return api;
+}
+
+struct ConvGeom {
+    int mn[3];       // smallest source coordinate per axis
+    int S[3];        // extent of the sources' bounding box
+    int L[3];        // outputs per axis: 0 .. L-1, same frame as the source coordinates
+    int P[3];        // transform lengths
+};
+
+__global__ void k_conv_bbox(const FieldSource* __restrict__ src, const uint32_t* __restrict__ count_p, int* __restrict__ box) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *count_p) return;
+    const FieldSource s = src[k];
+    atomicMin(box + 0, (int)s.x); atomicMin(box + 1, (int)s.y); atomicMin(box + 2, (int)s.z);
+    atomicMax(box + 3, (int)s.x); atomicMax(box + 4, (int)s.y); atomicMax(box + 5, (int)s.z);
+}
+// component `comp` (0..2: mx, my, mz; the charge of static_e sits in mx) of every source into the zeroed real array
+__global__ void k_conv_scatter(const FieldSource* __restrict__ src, const uint32_t* __restrict__ count_p, const int comp, const __grid_constant__ ConvGeom g,
+                               float* __restrict__ R) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *count_p) return;
+    const FieldSource s = src[k];
+    const size_t i = ((size_t)((int)s.z - g.mn[2]) * g.P[1] + (size_t)((int)s.y - g.mn[1])) * g.P[0] + (size_t)((int)s.x - g.mn[0]);
+    R[i] = comp == 0 ? s.mx : comp == 1 ? s.my : s.mz;
+}
+// K[j mod P] = G_comp(j - min) for j in [-(S-1), L-1], zero elsewhere and at d = 0 (the sums skip l == 0, sim.cl:1245, :1293)
+__global__ void __launch_bounds__(128) k_conv_kernel(const int comp, const __grid_constant__ ConvGeom g, float* __restrict__ R) {
+    const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y, iz = blockIdx.z;
+    if (ix >= g.P[0]) return;
+    const int jx = ix < g.L[0] ? ix : ix - g.P[0], jy = iy < g.L[1] ? iy : iy - g.P[1], jz = iz < g.L[2] ? iz : iz - g.P[2];
+    float v = 0.0f;
+    if (jx > -g.S[0] && jy > -g.S[1] && jz > -g.S[2]) {
+        const float dx = (float)(jx - g.mn[0]), dy = (float)(jy - g.mn[1]), dz = (float)(jz - g.mn[2]);  // integers below 2^12: r2 is exact
+        const float r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 > 0.0f) v = (comp == 0 ? dx : comp == 1 ? dy : dz) / (r2 * sqrtf(r2));
+    }
+    R[((size_t)iz * g.P[1] + iy) * g.P[0] + ix] = v;
+}
+// out = (accumulate ? out : 0) + A * B
+__global__ void k_conv_mac(const float2* __restrict__ A, const float2* __restrict__ B, float2* __restrict__ out, const size_t n, const int accumulate) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 a = A[i], b = B[i];
+        float2 r = make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+        if (accumulate) { const float2 o = out[i]; r.x += o.x; r.y += o.y; }
+        out[i] = r;
+    }
+}
+__global__ void k_conv_psi_out(const float* __restrict__ R, const __grid_constant__ ConvGeom g, const float scale, float* __restrict__ psi) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= g.L[0]) return;
+    psi[((size_t)z * g.L[1] + y) * g.L[0] + x] = R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale;
+}
+// E[comp] += ke * sum for every fluid cell that is not a halo cell (sim.cl:1281-1284, :1297-1299)
+__global__ void k_conv_e_out(const __grid_constant__ KArgs a, const float* __restrict__ R, const __grid_constant__ ConvGeom g, const int comp, const float scale,
+                             float* __restrict__ E) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+    if (x >= a.nx || is_halo(a, x, y, z)) return;
+    const uint64_t n = x + (y + (uint64_t)z * a.ny) * a.nx;
+    if ((a.flags[n] & ION_TYPE_S) == ION_TYPE_S) return;
+    E[(uint64_t)comp * a.N + n] += (R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale) * a.ke;
+}
+
+static int smooth7(int n) {  // smallest length >= n whose prime factors are 2, 3, 5, 7
+    for (;; n++) {
+        int m = n;
+        for (int p : {2, 3, 5, 7})
+            while (m % p == 0) m /= p;
+        if (m == 1) return n;
+    }
+}
+
+// which = 0: psi on the padded (n+2)^3 grid into a.E_dyn followed by static_b; which != 0: static E into `E`.
+// Returns cudaErrorNotSupported with *why set when cuFFT or the memory for the transforms is not available.
+cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t* counts, void* table, uint32_t total, cudaStream_t s, uint64_t* launches,
+                                  const char** why) {
+    *why = nullptr;
+    const CufftApi& fft = cufft_api();
+    if (!fft.ok) { *why = "cuFFT could not be loaded (libcufft.so.11)"; return cudaErrorNotSupported; }
+    FieldSource* src = reinterpret_cast<FieldSource*>(table);
+    const uint32_t nblocks = (uint32_t)((a.N + CP_BLOCK - 1) / CP_BLOCK);
+    const uint32_t* count_p = counts + nblocks;
+    cudaError_t e = which == 0 ? compact(a, ION_TYPE_M, counts, src, a.B_dyn, 1, 1.0f, s) : compact(a, ION_TYPE_F | ION_TYPE_C, counts, src, a.B_dyn, 0, 0.0f, s);
+    if (e != cudaSuccess) return e;
+    *launches += 3;
+    ConvGeom g;
+    const int pad = which == 0 ? 2 : 0;
+    g.L[0] = (int)a.nx + pad; g.L[1] = (int)a.ny + pad; g.L[2] = (int)a.nz + pad;
+    int* box = nullptr;
+    int hbox[6] = {INT_MAX, INT_MAX, INT_MAX, -1, -1, -1};
+    e = cudaMallocAsync((void**)&box, sizeof(hbox), s);
+    if (e != cudaSuccess) return e;
+    cudaMemcpyAsync(box, hbox, sizeof(hbox), cudaMemcpyHostToDevice, s);
+    k_conv_bbox<<<(total + 255u) / 256u, 256, 0, s>>>(src, count_p, box);
+    cudaMemcpyAsync(hbox, box, sizeof(hbox), cudaMemcpyDeviceToHost, s);
+    cudaFreeAsync(box, s);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return e;
+    *launches += 1;
+    size_t real_n = 1, cplx_n = 1;
+    for (int i = 0; i < 3; i++) {
+        g.mn[i] = hbox[i];
+        g.S[i] = hbox[3 + i] - hbox[i] + 1;
+        g.P[i] = smooth7(g.L[i] + g.S[i] - 1);
+        real_n *= (size_t)g.P[i];
+        cplx_n *= (size_t)(i == 0 ? g.P[0] / 2 + 1 : g.P[i]);
+    }
+    size_t free_b = 0, total_b = 0;
+    cudaMemGetInfo(&free_b, &total_b);
+    const size_t need = real_n * sizeof(float) + 3 * cplx_n * sizeof(float2);
+    if (need * 2 > free_b) { *why = "not enough free device memory for the transforms of the FFT precompute mode"; return cudaErrorNotSupported; }
+    float* R = nullptr;
+    float2 *A = nullptr, *B = nullptr, *C = nullptr;
+    cufftHandle fwd = 0, inv = 0;
+    bool have_fwd = false, have_inv = false;
+    auto cleanup = [&]() {
+        if (have_fwd) fft.Destroy(fwd);
+        if (have_inv) fft.Destroy(inv);
+        cudaFree(R); cudaFree(A); cudaFree(B); cudaFree(C);
+    };
+    e = cudaMalloc((void**)&R, real_n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&A, cplx_n * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B, cplx_n * sizeof(float2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&C, cplx_n * sizeof(float2));
+    if (e != cudaSuccess) { cleanup(); return e; }
+    // cuFFT: the LAST dimension varies fastest
+    have_fwd = fft.Plan3d(&fwd, g.P[2], g.P[1], g.P[0], CUFFT_R2C) == CUFFT_SUCCESS;
+    have_inv = have_fwd && fft.Plan3d(&inv, g.P[2], g.P[1], g.P[0], CUFFT_C2R) == CUFFT_SUCCESS;
+    if (!have_fwd || !have_inv || fft.SetStream(fwd, s) != CUFFT_SUCCESS || fft.SetStream(inv, s) != CUFFT_SUCCESS) {
+        cleanup();
+        *why = "cufftPlan3d failed (transform lengths or work-area memory)";
+        return cudaErrorNotSupported;
+    }
+    const dim3 gk((unsigned)(g.P[0] + 127) / 128, (unsigned)g.P[1], (unsigned)g.P[2]);
+    const unsigned mac_blocks = (unsigned)((cplx_n + 255) / 256 < 148 * 16 ? (cplx_n + 255) / 256 : 148 * 16);
+    const float norm = 1.0f / ((float)g.P[0] * (float)g.P[1] * (float)g.P[2]);
+    bool ok = true;
+    auto forward_source = [&](int comp) {
+        cudaMemsetAsync(R, 0, real_n * sizeof(float), s);
+        k_conv_scatter<<<(total + 255u) / 256u, 256, 0, s>>>(src, count_p, comp, g, R);
+        ok = ok && fft.ExecR2C(fwd, R, A) == CUFFT_SUCCESS;
+    };
+    auto forward_kernel = [&](int comp) {
+        k_conv_kernel<<<gk, 128, 0, s>>>(comp, g, R);
+        ok = ok && fft.ExecR2C(fwd, R, B) == CUFFT_SUCCESS;
+    };
+    if (which == 0) {
+        for (int c = 0; c < 3; c++) {
+            forward_source(c);
+            forward_kernel(c);
+            k_conv_mac<<<mac_blocks, 256, 0, s>>>(A, B, C, cplx_n, c > 0 ? 1 : 0);
+        }
+        ok = ok && fft.ExecC2R(inv, C, R) == CUFFT_SUCCESS;
+        k_conv_psi_out<<<dim3((unsigned)(g.L[0] + 127) / 128, (unsigned)g.L[1], (unsigned)g.L[2]), 128, 0, s>>>(R, g, norm * 0.07957747154594767f, a.E_dyn);
+        unsigned b = ((a.nx + 31u) / 32u) * 32u;
+        if (b > 128u) b = 128u;
+        k_static_b<<<dim3((a.nx + b - 1u) / b, a.ny, a.nz), b, 0, s>>>(a, a.E_dyn);
+        *launches += 11;  // own kernels; the transforms are library launches
+    } else {
+        forward_source(0);
+        for (int c = 0; c < 3; c++) {
+            forward_kernel(c);
+            k_conv_mac<<<mac_blocks, 256, 0, s>>>(A, B, C, cplx_n, 0);
+            ok = ok && fft.ExecC2R(inv, C, R) == CUFFT_SUCCESS;
+            k_conv_e_out<<<dim3((a.nx + 127u) / 128u, a.ny, a.nz), 128, 0, s>>>(a, R, g, c, norm, E);
+        }
+        *launches += 10;
+    }
+    e = cudaGetLastError();
+    const cudaError_t e2 = cudaStreamSynchronize(s);  // the work arrays are freed below
+    cleanup();
+    if (!ok) { *why = "a cuFFT transform failed"; return cudaErrorNotSupported; }
+    return e != cudaSuccess ? e : e2;
 }
 
 }  // namespace ion

@@ -469,6 +469,37 @@ def test_fast_precompute_mode(golden, gpu_lib):
     assert not same_bits(out[1][0], out[0][0])  # the fast kernel really ran
 
 
+def test_fft_precompute_mode(golden, gpu_lib):
+    """ion_domain_set_precompute_mode(2): psi_from_mesh and static_e_from_mesh as zero-padded FFT convolutions of the source cells with
+    d / |d|^3 (mesh_kernels.cu, cuFFT transforms).  Same sums in a different order with FP32 transforms: psi and E_stat within 2e-5
+    relative L2 of the exact mode; B_stat -- central differences of psi, which amplify the transform's white noise -- within 2e-3."""
+    from ionsolver_b200 import lbm as L
+    g = golden["voxelize"]
+    out = {}
+    for mode in (0, 2):
+        cfg = rh.RefConfig(velocity_set="D3Q19", float_type="FP32", n_x=48, n_y=40, n_z=44, nu=0.05, ext_volume_force=True,
+                           ext_magneto_hydro=True, mhd_lod_depth=2)
+        cfg.units.set(48.0, 1.0, 1.0, 1.0, 1.0, 0.1, 1.0, 1.2250, 1e-10, 1.0)
+        gpu = product(cfg)
+        kind = {"Solid": L.ModelType.Solid, "Magnet": L.ModelType.Magnet, "Charged": L.ModelType.Charged, "ChargedECR": L.ModelType.ChargedECR}
+        for i, (f, k, val, origin) in enumerate(g["config"]["meshes"]):
+            gpu.import_mesh(os.path.join(cases.STL_DIR, f), 1.0, origin[0], origin[1], origin[2], 0.0, 0.0, 0.0)
+            gpu.voxelise_mesh(i, kind[k], val)
+        for d in gpu.domains:
+            d.set_precompute_mode(mode)
+        gpu.precompute_B()
+        d = gpu.domains[0]
+        psi = d.read(cases.FIELD_OF["e_dyn"])[: (cfg.n_x + 2) * (cfg.n_y + 2) * (cfg.n_z + 2)].copy()
+        gpu.precompute_E()
+        out[mode] = (psi, d.read(cases.FIELD_OF["b_stat"]).copy(), d.read(cases.FIELD_OF["e_stat"]).copy())
+        gpu.close()
+    assert sha(out[0][0]) == g["psi"]["sha256"]  # the exact mode is the reference's result
+    err = [rel_l2(out[2][i], out[0][i]) for i in range(3)]
+    assert float(np.abs(out[0][2]).max()) > 0.0, "the scene must hold charged cells for the E_stat half of the test"
+    assert err[0] < 2e-5 and err[1] < 2e-3 and err[2] < 2e-5, err
+    assert not same_bits(out[2][0], out[0][0])  # the FFT path really ran
+
+
 def test_reference_stl_assets_through_the_cuda_voxeliser(golden, gpu_lib):
     """The reference's own STL files (stl/*.stl, copied to tests/golden/stl/ref as fixtures) through the CUDA voxeliser and
     static-field kernels, against SHA-256 of what the reference's kernels produce (tests/golden/make_golden.py::ref_stl_vectors):
