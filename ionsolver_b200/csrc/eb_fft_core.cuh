@@ -621,8 +621,9 @@ ION_HD void far_accumulate(float x0, float y0, float z0, const FarSource& s, flo
         }
     }
 }
-// value of component i (0..2 = E, 3..5 = B) of the polynomial at offset (dx, dy, dz) from the block centre; `t` = the 30 entries of
-// the E or B part
+// value of component i (0..2) of the polynomial at offset (dx, dy, dz) from the block centre; `t` = the 30 entries of the E or B
+// part.  The full form, kept as the definition: k_eb_combine evaluates the same polynomial after reducing it to a + dx (b + c dx)
+// per (row, block), since dy and dz are constant along a row.
 ION_HD float far_eval(const float* t, int i, float dx, float dy, float dz) {
     const float* G = t + 3 + 3 * i;
     const float* H = t + 12 + 6 * i;

@@ -429,15 +429,17 @@ cudaError_t launch_precompute_e(const KArgs& a, float* E, uint32_t* counts, void
 // 7-smooth length: with K[j mod P] = G(j - min) for j in [-(S-1), L-1] the circular convolution of the box-relative sources with K
 // has no wrap-around on the L outputs.  The transforms are plain library FFTs (cuFFT R2C / C2R, bound at run time so that the library
 // loads without it) off the time-step path; source scatter, kernel sampling, spectral products and the write-back are kernels here.
-// Same sum in a different order and FP32 transforms: ~1e-6 of the largest |psi| everywhere -- relative to the LOCAL field that is more
-// than the direct modes' rounding far away from the sources, which is why the mode is opt-in and has its own tolerance test.
+// Everything between the FP32 inputs and the FP32 result is double precision (D2Z / Z2D transforms, kernel samples, products): FP32
+// transforms leave white noise of ~1e-6 of the LARGEST |psi| everywhere, which the central differences of static_b_from_mesh turn
+// into 1e-3 of B_stat; in FP64 the mode returns the correctly rounded sum, i.e. it differs from the reference-order FP32 sum by that
+// sum's own rounding only.  Opt-in because the result is not bit-identical to the reference's.
 // ------------------------------------------------------------------------------------------------------------------------------
 struct CufftApi {
     bool ok;
     cufftResult (*Plan3d)(cufftHandle*, int, int, int, cufftType);
     cufftResult (*SetStream)(cufftHandle, cudaStream_t);
-    cufftResult (*ExecR2C)(cufftHandle, cufftReal*, cufftComplex*);
-    cufftResult (*ExecC2R)(cufftHandle, cufftComplex*, cufftReal*);
+    cufftResult (*ExecD2Z)(cufftHandle, cufftDoubleReal*, cufftDoubleComplex*);
+    cufftResult (*ExecZ2D)(cufftHandle, cufftDoubleComplex*, cufftDoubleReal*);
     cufftResult (*Destroy)(cufftHandle);
 };
 static const CufftApi& cufft_api() {
@@ -451,10 +453,10 @@ static const CufftApi& cufft_api() {
         if (!h) return a;
         *(void**)(&a.Plan3d) = dlsym(h, "cufftPlan3d");
         *(void**)(&a.SetStream) = dlsym(h, "cufftSetStream");
-        *(void**)(&a.ExecR2C) = dlsym(h, "cufftExecR2C");
-        *(void**)(&a.ExecC2R) = dlsym(h, "cufftExecC2R");
+        *(void**)(&a.ExecD2Z) = dlsym(h, "cufftExecD2Z");
+        *(void**)(&a.ExecZ2D) = dlsym(h, "cufftExecZ2D");
         *(void**)(&a.Destroy) = dlsym(h, "cufftDestroy");
-        a.ok = a.Plan3d && a.SetStream && a.ExecR2C && a.ExecC2R && a.Destroy;
+        a.ok = a.Plan3d && a.SetStream && a.ExecD2Z && a.ExecZ2D && a.Destroy;
         return a;
     }();
     return api;
@@ -476,48 +478,48 @@ __global__ void k_conv_bbox(const FieldSource* __restrict__ src, const uint32_t*
 }
 // component `comp` (0..2: mx, my, mz; the charge of static_e sits in mx) of every source into the zeroed real array
 __global__ void k_conv_scatter(const FieldSource* __restrict__ src, const uint32_t* __restrict__ count_p, const int comp, const __grid_constant__ ConvGeom g,
-                               float* __restrict__ R) {
+                               double* __restrict__ R) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= *count_p) return;
     const FieldSource s = src[k];
     const size_t i = ((size_t)((int)s.z - g.mn[2]) * g.P[1] + (size_t)((int)s.y - g.mn[1])) * g.P[0] + (size_t)((int)s.x - g.mn[0]);
-    R[i] = comp == 0 ? s.mx : comp == 1 ? s.my : s.mz;
+    R[i] = (double)(comp == 0 ? s.mx : comp == 1 ? s.my : s.mz);
 }
 // K[j mod P] = G_comp(j - min) for j in [-(S-1), L-1], zero elsewhere and at d = 0 (the sums skip l == 0, sim.cl:1245, :1293)
-__global__ void __launch_bounds__(128) k_conv_kernel(const int comp, const __grid_constant__ ConvGeom g, float* __restrict__ R) {
+__global__ void __launch_bounds__(128) k_conv_kernel(const int comp, const __grid_constant__ ConvGeom g, double* __restrict__ R) {
     const int ix = blockIdx.x * blockDim.x + threadIdx.x, iy = blockIdx.y, iz = blockIdx.z;
     if (ix >= g.P[0]) return;
     const int jx = ix < g.L[0] ? ix : ix - g.P[0], jy = iy < g.L[1] ? iy : iy - g.P[1], jz = iz < g.L[2] ? iz : iz - g.P[2];
-    float v = 0.0f;
+    double v = 0.0;
     if (jx > -g.S[0] && jy > -g.S[1] && jz > -g.S[2]) {
-        const float dx = (float)(jx - g.mn[0]), dy = (float)(jy - g.mn[1]), dz = (float)(jz - g.mn[2]);  // integers below 2^12: r2 is exact
-        const float r2 = dx * dx + dy * dy + dz * dz;
-        if (r2 > 0.0f) v = (comp == 0 ? dx : comp == 1 ? dy : dz) / (r2 * sqrtf(r2));
+        const double dx = (double)(jx - g.mn[0]), dy = (double)(jy - g.mn[1]), dz = (double)(jz - g.mn[2]);
+        const double r2 = dx * dx + dy * dy + dz * dz;
+        if (r2 > 0.0) v = (comp == 0 ? dx : comp == 1 ? dy : dz) / (r2 * sqrt(r2));
     }
     R[((size_t)iz * g.P[1] + iy) * g.P[0] + ix] = v;
 }
 // out = (accumulate ? out : 0) + A * B
-__global__ void k_conv_mac(const float2* __restrict__ A, const float2* __restrict__ B, float2* __restrict__ out, const size_t n, const int accumulate) {
+__global__ void k_conv_mac(const double2* __restrict__ A, const double2* __restrict__ B, double2* __restrict__ out, const size_t n, const int accumulate) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float2 a = A[i], b = B[i];
-        float2 r = make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-        if (accumulate) { const float2 o = out[i]; r.x += o.x; r.y += o.y; }
+        const double2 a = A[i], b = B[i];
+        double2 r = make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+        if (accumulate) { const double2 o = out[i]; r.x += o.x; r.y += o.y; }
         out[i] = r;
     }
 }
-__global__ void k_conv_psi_out(const float* __restrict__ R, const __grid_constant__ ConvGeom g, const float scale, float* __restrict__ psi) {
+__global__ void k_conv_psi_out(const double* __restrict__ R, const __grid_constant__ ConvGeom g, const double scale, float* __restrict__ psi) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
     if (x >= g.L[0]) return;
-    psi[((size_t)z * g.L[1] + y) * g.L[0] + x] = R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale;
+    psi[((size_t)z * g.L[1] + y) * g.L[0] + x] = (float)(R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale);
 }
 // E[comp] += ke * sum for every fluid cell that is not a halo cell (sim.cl:1281-1284, :1297-1299)
-__global__ void k_conv_e_out(const __grid_constant__ KArgs a, const float* __restrict__ R, const __grid_constant__ ConvGeom g, const int comp, const float scale,
+__global__ void k_conv_e_out(const __grid_constant__ KArgs a, const double* __restrict__ R, const __grid_constant__ ConvGeom g, const int comp, const double scale,
                              float* __restrict__ E) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
     if (x >= a.nx || is_halo(a, x, y, z)) return;
     const uint64_t n = x + (y + (uint64_t)z * a.ny) * a.nx;
     if ((a.flags[n] & ION_TYPE_S) == ION_TYPE_S) return;
-    E[(uint64_t)comp * a.N + n] += (R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale) * a.ke;
+    E[(uint64_t)comp * a.N + n] += (float)(R[((size_t)z * g.P[1] + y) * g.P[0] + x] * scale) * a.ke;  // the rounded sum, then * ke like sim.cl:1297
 }
 
 static int smooth7(int n) {  // smallest length >= n whose prime factors are 2, 3, 5, 7
@@ -566,10 +568,10 @@ cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t*
     }
     size_t free_b = 0, total_b = 0;
     cudaMemGetInfo(&free_b, &total_b);
-    const size_t need = real_n * sizeof(float) + 3 * cplx_n * sizeof(float2);
+    const size_t need = real_n * sizeof(double) + 3 * cplx_n * sizeof(double2);
     if (need * 2 > free_b) { *why = "not enough free device memory for the transforms of the FFT precompute mode"; return cudaErrorNotSupported; }
-    float* R = nullptr;
-    float2 *A = nullptr, *B = nullptr, *C = nullptr;
+    double* R = nullptr;
+    double2 *A = nullptr, *B = nullptr, *C = nullptr;
     cufftHandle fwd = 0, inv = 0;
     bool have_fwd = false, have_inv = false;
     auto cleanup = [&]() {
@@ -577,14 +579,14 @@ cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t*
         if (have_inv) fft.Destroy(inv);
         cudaFree(R); cudaFree(A); cudaFree(B); cudaFree(C);
     };
-    e = cudaMalloc((void**)&R, real_n * sizeof(float));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&A, cplx_n * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&B, cplx_n * sizeof(float2));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&C, cplx_n * sizeof(float2));
+    e = cudaMalloc((void**)&R, real_n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&A, cplx_n * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&B, cplx_n * sizeof(double2));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&C, cplx_n * sizeof(double2));
     if (e != cudaSuccess) { cleanup(); return e; }
     // cuFFT: the LAST dimension varies fastest
-    have_fwd = fft.Plan3d(&fwd, g.P[2], g.P[1], g.P[0], CUFFT_R2C) == CUFFT_SUCCESS;
-    have_inv = have_fwd && fft.Plan3d(&inv, g.P[2], g.P[1], g.P[0], CUFFT_C2R) == CUFFT_SUCCESS;
+    have_fwd = fft.Plan3d(&fwd, g.P[2], g.P[1], g.P[0], CUFFT_D2Z) == CUFFT_SUCCESS;
+    have_inv = have_fwd && fft.Plan3d(&inv, g.P[2], g.P[1], g.P[0], CUFFT_Z2D) == CUFFT_SUCCESS;
     if (!have_fwd || !have_inv || fft.SetStream(fwd, s) != CUFFT_SUCCESS || fft.SetStream(inv, s) != CUFFT_SUCCESS) {
         cleanup();
         *why = "cufftPlan3d failed (transform lengths or work-area memory)";
@@ -592,16 +594,16 @@ cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t*
     }
     const dim3 gk((unsigned)(g.P[0] + 127) / 128, (unsigned)g.P[1], (unsigned)g.P[2]);
     const unsigned mac_blocks = (unsigned)((cplx_n + 255) / 256 < 148 * 16 ? (cplx_n + 255) / 256 : 148 * 16);
-    const float norm = 1.0f / ((float)g.P[0] * (float)g.P[1] * (float)g.P[2]);
+    const double norm = 1.0 / ((double)g.P[0] * (double)g.P[1] * (double)g.P[2]);
     bool ok = true;
     auto forward_source = [&](int comp) {
-        cudaMemsetAsync(R, 0, real_n * sizeof(float), s);
+        cudaMemsetAsync(R, 0, real_n * sizeof(double), s);
         k_conv_scatter<<<(total + 255u) / 256u, 256, 0, s>>>(src, count_p, comp, g, R);
-        ok = ok && fft.ExecR2C(fwd, R, A) == CUFFT_SUCCESS;
+        ok = ok && fft.ExecD2Z(fwd, R, reinterpret_cast<cufftDoubleComplex*>(A)) == CUFFT_SUCCESS;
     };
     auto forward_kernel = [&](int comp) {
         k_conv_kernel<<<gk, 128, 0, s>>>(comp, g, R);
-        ok = ok && fft.ExecR2C(fwd, R, B) == CUFFT_SUCCESS;
+        ok = ok && fft.ExecD2Z(fwd, R, reinterpret_cast<cufftDoubleComplex*>(B)) == CUFFT_SUCCESS;
     };
     if (which == 0) {
         for (int c = 0; c < 3; c++) {
@@ -609,8 +611,8 @@ cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t*
             forward_kernel(c);
             k_conv_mac<<<mac_blocks, 256, 0, s>>>(A, B, C, cplx_n, c > 0 ? 1 : 0);
         }
-        ok = ok && fft.ExecC2R(inv, C, R) == CUFFT_SUCCESS;
-        k_conv_psi_out<<<dim3((unsigned)(g.L[0] + 127) / 128, (unsigned)g.L[1], (unsigned)g.L[2]), 128, 0, s>>>(R, g, norm * 0.07957747154594767f, a.E_dyn);
+        ok = ok && fft.ExecZ2D(inv, reinterpret_cast<cufftDoubleComplex*>(C), R) == CUFFT_SUCCESS;
+        k_conv_psi_out<<<dim3((unsigned)(g.L[0] + 127) / 128, (unsigned)g.L[1], (unsigned)g.L[2]), 128, 0, s>>>(R, g, norm / (4.0 * 3.14159265358979323846), a.E_dyn);
         unsigned b = ((a.nx + 31u) / 32u) * 32u;
         if (b > 128u) b = 128u;
         k_static_b<<<dim3((a.nx + b - 1u) / b, a.ny, a.nz), b, 0, s>>>(a, a.E_dyn);
@@ -620,7 +622,7 @@ cudaError_t launch_precompute_fft(const KArgs& a, int which, float* E, uint32_t*
         for (int c = 0; c < 3; c++) {
             forward_kernel(c);
             k_conv_mac<<<mac_blocks, 256, 0, s>>>(A, B, C, cplx_n, 0);
-            ok = ok && fft.ExecC2R(inv, C, R) == CUFFT_SUCCESS;
+            ok = ok && fft.ExecZ2D(inv, reinterpret_cast<cufftDoubleComplex*>(C), R) == CUFFT_SUCCESS;
             k_conv_e_out<<<dim3((a.nx + 127u) / 128u, a.ny, a.nz), 128, 0, s>>>(a, R, g, c, norm, E);
         }
         *launches += 10;

@@ -471,8 +471,9 @@ def test_fast_precompute_mode(golden, gpu_lib):
 
 def test_fft_precompute_mode(golden, gpu_lib):
     """ion_domain_set_precompute_mode(2): psi_from_mesh and static_e_from_mesh as zero-padded FFT convolutions of the source cells with
-    d / |d|^3 (mesh_kernels.cu, cuFFT transforms).  Same sums in a different order with FP32 transforms: psi and E_stat within 2e-5
-    relative L2 of the exact mode; B_stat -- central differences of psi, which amplify the transform's white noise -- within 2e-3."""
+    d / |d|^3 (mesh_kernels.cu, cuFFT D2Z / Z2D transforms).  Double precision between the FP32 inputs and the FP32 result, so the
+    mode returns the correctly rounded sums: it differs from the exact mode by the rounding of the reference's sequential FP32 sum
+    only -- the same bounds as the fast direct mode: psi and E_stat within 1e-5 relative L2, B_stat (central differences) within 1e-4."""
     from ionsolver_b200 import lbm as L
     g = golden["voxelize"]
     out = {}
@@ -496,7 +497,8 @@ def test_fft_precompute_mode(golden, gpu_lib):
     assert sha(out[0][0]) == g["psi"]["sha256"]  # the exact mode is the reference's result
     err = [rel_l2(out[2][i], out[0][i]) for i in range(3)]
     assert float(np.abs(out[0][2]).max()) > 0.0, "the scene must hold charged cells for the E_stat half of the test"
-    assert err[0] < 2e-5 and err[1] < 2e-3 and err[2] < 2e-5, err
+    print("FFT precompute mode vs reference order, relative L2 (psi, B_stat, E_stat):", err)
+    assert err[0] < 1e-5 and err[1] < 1e-4 and err[2] < 1e-5, err
     assert not same_bits(out[2][0], out[0][0])  # the FFT path really ran
 
 
