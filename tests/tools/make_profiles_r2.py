@@ -190,6 +190,23 @@ def main():
     d = first_existing("r2_final_drift.jsonl", "r2c_drift.jsonl")
     if d:
         drift(d)
+    # the other configurations, the reference arm, the test logs: copied under fixed names
+    for src, dst in (("r2_final_bench_cfg1.json", "r2_bench_cfg1.json"), ("r2_final_bench_cfg3.json", "r2_bench_cfg3.json"),
+                     ("r2_final_bench_cfg4.json", "r2_bench_cfg4.json"), ("r2_final_bench_lod3.json", "r2_bench_lod3.json"),
+                     ("r2_final_bench_reference.json", "r2_bench_reference_arm.json")):
+        p = first_existing(src)
+        if p and load_line(p):
+            json.dump(load_line(p), open(os.path.join(PRO, dst), "w"), indent=1)
+    for src, dst in (("r2_final_pytest.log", "r2_pytest_gpu_1gpu.log"), ("r2_final_pytest_2gpus.log", "r2_pytest_gpu_2gpus.log"),
+                     ("r2q_cfg1_launches.csv", "r2_cfg1_launches_raw.csv")):
+        p = first_existing(src)
+        if p:
+            shutil.copy(p, os.path.join(PRO, dst))
+    big = [load_line(p) for p in (first_existing("r2_final_cfg4_n8.json"), first_existing("r2_final_cfg5_n8.json"), first_existing("r2_final_bench_cfg4.json")) if p]
+    if len(big) == 3:
+        with open(os.path.join(PRO, "r2_scaling_cfg4_cfg5_n8.jsonl"), "w") as f:
+            for j in big:
+                f.write(json.dumps(j) + "\n")
     print("profiles written:", sorted(f for f in os.listdir(PRO) if f.startswith("r2_")))
 
 
