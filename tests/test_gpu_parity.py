@@ -626,6 +626,10 @@ def test_error_behaviour(gpu_lib):
     with pytest.raises(capi.IonError) as e:
         d.write(capi.FIELD_RHO, np.zeros(8 * 8 * 8 + 1, np.float32))
     assert e.value.code == capi.ION_ERR_RANGE
+    for mode in (-1, 3):  # 0 reference order, 1 fast direct sum, 2 FFT convolution
+        with pytest.raises(capi.IonError) as e:
+            d.set_precompute_mode(mode)
+        assert e.value.code == capi.ION_ERR_INVALID
     plain.close()
     bad = [dict(ext_magneto_hydro=True),                                              # MHD without VOLUME_FORCE does not compile in the reference
            dict(ext_magneto_hydro=True, ext_volume_force=True, mhd_lod_depth=5),      # 1<<(1<<5) shifts out of range
