@@ -255,11 +255,11 @@ __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom
             const float G0 = G[0], G1 = G[far_blocks], G2 = G[2 * (size_t)far_blocks];
             const float H0 = H[0], H1 = H[far_blocks], H2 = H[2 * (size_t)far_blocks], H3 = H[3 * (size_t)far_blocks], H4 = H[4 * (size_t)far_blocks],
                         H5 = H[5 * (size_t)far_blocks];
-            float a0 = fmaf(G1, dy, fmaf(G2, dz, F0));
-            a0 = fmaf(0.5f * H3, dy * dy, fmaf(H4, dy * dz, fmaf(0.5f * H5, dz * dz, a0)));
-            ftile[(size_t)(3u * o) * far_nbx + bx] = a0;
-            ftile[(size_t)(3u * o + 1u) * far_nbx + bx] = fmaf(H1, dy, fmaf(H2, dz, G0));
-            ftile[(size_t)(3u * o + 2u) * far_nbx + bx] = 0.5f * H0;
+            float pa, pb, pc;
+            far_reduce_x(F0, G0, G1, G2, H0, H1, H2, H3, H4, H5, dy, dz, pa, pb, pc);
+            ftile[(size_t)(3u * o) * far_nbx + bx] = pa;
+            ftile[(size_t)(3u * o + 1u) * far_nbx + bx] = pb;
+            ftile[(size_t)(3u * o + 2u) * far_nbx + bx] = pc;
         }
     }
     constexpr int R = CH > 0 ? CH : 1;
@@ -309,7 +309,7 @@ __global__ void __launch_bounds__(256) k_eb_combine(const __grid_constant__ Geom
                 const float* q = ftile + x / FARB;
 #pragma unroll
                 for (int o = 0; o < 6; o++)
-                    sum[o] += fmaf(fdx, fmaf(q[(size_t)(3 * o + 2) * far_nbx], fdx, q[(size_t)(3 * o + 1) * far_nbx]), q[(size_t)(3 * o) * far_nbx]);
+                    sum[o] += far_eval_x(q[(size_t)(3 * o) * far_nbx], q[(size_t)(3 * o + 1) * far_nbx], q[(size_t)(3 * o + 2) * far_nbx], fdx);
             }
 #pragma unroll
             for (int c = 0; c < 3; c++) {

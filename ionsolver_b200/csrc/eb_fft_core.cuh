@@ -633,6 +633,16 @@ ION_HD float far_eval(const float* t, int i, float dx, float dy, float dz) {
     v = fmaf(0.5f * H[3], dy * dy, fmaf(H[4], dy * dz, fmaf(0.5f * H[5], dz * dz, v)));
     return v;
 }
+// The same polynomial along a row of cells: dy and dz are constants there, so component i is a + dx (b + c dx).  F0, G[3], H[6] are
+// the entries of component i (any stride: the kernel reads them straight from the [FAR_T][blocks] table).
+ION_HD void far_reduce_x(float F0, float G0, float G1, float G2, float H0, float H1, float H2, float H3, float H4, float H5, float dy, float dz,
+                         float& a, float& b, float& c) {
+    float a0 = fmaf(G1, dy, fmaf(G2, dz, F0));
+    a = fmaf(0.5f * H3, dy * dy, fmaf(H4, dy * dz, fmaf(0.5f * H5, dz * dz, a0)));
+    b = fmaf(H1, dy, fmaf(H2, dz, G0));
+    c = 0.5f * H0;
+}
+ION_HD float far_eval_x(float a, float b, float c, float dx) { return fmaf(dx, fmaf(c, dx, b), a); }
 
 }  // namespace ebfft
 }  // namespace ion

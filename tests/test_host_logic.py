@@ -241,6 +241,78 @@ def test_polyphase_fft_field_update_on_cpu(tmp_path, args):
     assert res["rel_l2_E"] < 1e-6 and res["rel_l2_B"] < 1e-6 and res["untouched_bad"] == 0
 
 
+@pytest.mark.parametrize("farb,r_min,bound", [(8, 242.0, 1.6e-5), (4, 65.0, 6.4e-5)], ids=["8cubed_blocks", "4cubed_blocks"])
+def test_far_slab_taylor_path_on_cpu(tmp_path, farb, r_min, bound):
+    """Far slabs of update_e_b_dynamic (sim_kernels.cl:957-983, slabs two and more below): second-order Taylor tensors per FARB^3 block
+    of cells (eb_fft_core.cuh::far_accumulate), evaluated per cell in the row-reduced form a + dx (b + c dx) that k_eb_combine uses
+    (far_reduce_x / far_eval_x).  tests/tools/eb_far_emul.cpp runs those functions on the CPU at the smallest source distance the host
+    code admits for each block size (eb_fft.cu::far_set: R >= 40 x 6.06 for 8^3, R >= 25 x 2.6 for 4^3) against a double-precision
+    direct sum: error below the documented bound relative to the largest far-field value, and the reduced form equals the full one."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isfile(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not installed")
+    exe = tmp_path / "eb_far_emul"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I", cuda_inc, os.path.join(root, "tests", "tools", "eb_far_emul.cpp"),
+                    "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(farb), str(r_min)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert res["taylor_err_rel"] < bound and res["x_reduced_err_rel"] < bound and res["forms_differ_rel"] < 1e-6, res
+
+
+def test_fft_precompute_geometry_in_numpy():
+    """Index logic of the FFT precompute mode (mesh_kernels.cu::launch_precompute_fft), restated with numpy transforms: sources inside
+    their bounding box [mn, mn + S), outputs 0 .. L-1, transform lengths P = smooth7(L + S - 1), kernel array K[j mod P] = G(j - mn) for
+    j in [-(S-1), L-1] and zero elsewhere / at d = 0.  The circular convolution then equals the direct sum of M . d / |d|^3 on every
+    output (no wrap-around), for a box that touches the lattice edge as well."""
+    rng = np.random.default_rng(1)
+
+    def smooth7(n):
+        while True:
+            m = n
+            for p in (2, 3, 5, 7):
+                while m % p == 0:
+                    m //= p
+            if m == 1:
+                return n
+            n += 1
+
+    assert [smooth7(n) for n in (1, 11, 13, 121, 515, 1031)] == [1, 12, 14, 125, 525, 1050]
+    for L, mn, S in ((np.array([14, 11, 9]), np.array([3, 2, 5]), np.array([4, 6, 3])), (np.array([8, 9, 10]), np.array([0, 0, 7]), np.array([8, 2, 3]))):
+        P = np.array([smooth7(int(L[i] + S[i] - 1)) for i in range(3)])
+        cells = {tuple(mn), tuple(mn + S - 1)}
+        while len(cells) < 12:
+            cells.add(tuple(int(v) for v in mn + rng.integers(0, S)))
+        src = [(np.array(c), rng.normal(size=3)) for c in sorted(cells)]
+        direct = np.zeros(L[::-1])
+        for z in range(L[2]):
+            for y in range(L[1]):
+                for x in range(L[0]):
+                    for c, m in src:
+                        d = np.array([x, y, z]) - c
+                        r2 = float((d * d).sum())
+                        if r2 > 0:
+                            direct[z, y, x] += float(d @ m) / r2 ** 1.5
+        acc = np.zeros((P[2], P[1], P[0] // 2 + 1), complex)
+        idx = [np.arange(P[a]) for a in range(3)]
+        j = [np.where(idx[a] < L[a], idx[a], idx[a] - P[a]) for a in range(3)]
+        jz, jy, jx = np.meshgrid(j[2], j[1], j[0], indexing="ij")
+        valid = (jx > -S[0]) & (jy > -S[1]) & (jz > -S[2])
+        d = [jx - mn[0], jy - mn[1], jz - mn[2]]
+        r2 = (d[0] ** 2 + d[1] ** 2 + d[2] ** 2).astype(float)
+        inv = np.where(r2 > 0, 1.0 / np.maximum(r2, 1.0) ** 1.5, 0.0) * valid
+        for comp in range(3):
+            R = np.zeros(P[::-1])
+            for c, m in src:
+                R[c[2] - mn[2], c[1] - mn[1], c[0] - mn[0]] = m[comp]
+            acc += np.fft.rfftn(R) * np.fft.rfftn(d[comp] * inv)
+        out = np.fft.irfftn(acc, s=tuple(int(v) for v in P[::-1]), axes=(0, 1, 2))[: L[2], : L[1], : L[0]]
+        assert np.abs(out - direct).max() < 1e-12 * max(1.0, np.abs(direct).max())
+
+
 def test_voxeliser_fill_rule_equals_the_reference_state_machine():
     """The CUDA voxeliser (mesh_kernels.cu) keeps the ray hits of a column as an XOR bitmap and fills by a closed form instead of
     the reference's sorted list + state machine (sim_kernels.cl:1194-1230).  Both rules, restated in Python, on 100 000 random hit
