@@ -37,7 +37,14 @@ struct EbFftPlan {
     // Kernel spectra.  Static mode (batch == ntasks): all of them, computed once.  Streamed mode (they do not fit the memory budget,
     // e.g. cfg5's 110 GB): a buffer for `batch` tasks per set, refilled by k_eb_khat in front of every k_eb_fft launch of a step
     // -- the field update then costs one forward and one inverse transform per task instead of an inverse one, and no memory.
-    uint32_t batch;
+    // Mirrored mode (whenever the full set does not fit, or ION_EB_FFT_MIRROR=1): a task with 2 ox > dsx reads the spectra of its
+    // partner with x offset dsx - ox at the reflected in-plane index (eb_fft_core.cuh, main_phase_product_mirror), so only the
+    // ~(dsx / 2 + 1) / dsx "canonical" tasks own a slot.  `batches`: the task array is laid out batch by batch, canonical tasks first
+    // (their position inside the batch = their slot), then the mirrored ones that read those slots.
+    uint32_t batch;  // slots of the buffer, per set
+    bool streamed;
+    struct Batch { uint32_t c0, nc, m0, nm; };
+    std::vector<Batch> batches;
     float2* khat;   // nsets * batch * khat_per_task
     float2* shat;   // nsets * shat_count
     float2* shatc;  // compact spectrum of set 1 (odd-position symmetry), shatc_count
@@ -112,7 +119,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
 // is hidden behind the FFT phases, and the products are formed in place where the copy landed.
 // NSETS = 2 (a slab with a lower neighbour): K^ of the neighbour's level D-1 pyramid is staged into the B slots instead of
 // s^_1..3, both source spectra are read from L2 in the product phase, and the two convolutions share every inverse transform.
-template <int ND, int NSETS>
+template <int ND, int NSETS, int MIRROR>
 __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     k_eb_fft(const __grid_constant__ Geom g, const Task* __restrict__ tasks, const float2* __restrict__ khat, const float2* __restrict__ shat,
              const float2* __restrict__ khat2, const float2* __restrict__ shat2c, float* __restrict__ scratch, const int accumulate) {
@@ -126,8 +133,8 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
     const int tid = threadIdx.x;
     if (tid < C::H * (ND / 2)) tw[tid] = main_tw4<ND>(tid / (ND / 2), tid % (ND / 2));
     const Task t = tasks[blockIdx.x];
-    const float2* kt = khat + (size_t)blockIdx.x * C::khat_per_task;
-    const float2* kt2 = NSETS == 2 ? khat2 + (size_t)blockIdx.x * C::khat_per_task : nullptr;
+    const float2* kt = khat + (size_t)t.kslot * C::khat_per_task;  // MIRROR: the partner's slot
+    const float2* kt2 = NSETS == 2 ? khat2 + (size_t)t.kslot * C::khat_per_task : nullptr;
     if (tid == 0) {
         mbar_init(&bars[0], 1u);
         mbar_init(&bars[1], 1u);
@@ -167,8 +174,13 @@ __global__ void __launch_bounds__(Cfg<ND>::T, 1)
         const int kx0 = it * C::P, np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
         float2* Wb = W + (size_t)(it & 1) * C::P * C::PLANE;
         mbar_wait(&bars[it & 1], (uint32_t)((it >> 1) & 1));
-        if (NSETS == 2) main_phase_product2<ND>(tid, shat, S0, kx0, np, Wb);
-        else main_phase_product<ND>(tid, S0, np, Wb);
+        if (NSETS == 2) {
+            if (MIRROR) main_phase_product2_mirror<ND>(tid, shat, S0, tw, kx0, np, Wb);
+            else main_phase_product2<ND>(tid, shat, S0, kx0, np, Wb);
+        } else {
+            if (MIRROR) main_phase_product_mirror<ND>(tid, S0, np, Wb);
+            else main_phase_product<ND>(tid, S0, np, Wb);
+        }
         __syncthreads();
         // Every thread is past the x accumulation of iteration it - 1 (which read the other buffer) and past this iteration's
         // products (which read S0): both are free, the operands of iteration it + 1 can land while this one is transformed.
@@ -390,9 +402,10 @@ void eb_fft_destroy(EbFftPlan* p) {
 template <int ND> static cudaError_t build_khat(EbFftPlan* p, cudaStream_t s) {
     cudaError_t e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
     if (e != cudaSuccess) return e;
-    if (p->batch < p->ntasks) return cudaSuccess;  // streamed mode: computed per batch inside every step
+    if (p->streamed) return cudaSuccess;  // computed per batch inside every step
+    const EbFftPlan::Batch& b = p->batches[0];  // static: one batch holds every slot
     for (int set = 0; set < p->nsets; set++)
-        k_eb_khat<ND><<<dim3(p->ntasks, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks, p->khat + (size_t)set * p->ntasks * Cfg<ND>::khat_per_task);
+        k_eb_khat<ND><<<dim3(b.nc, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks + b.c0, p->khat + (size_t)set * p->batch * Cfg<ND>::khat_per_task);
     return cudaGetLastError();
 }
 
@@ -475,18 +488,73 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     const size_t per = p->nd == 16 ? Cfg<16>::khat_per_task : Cfg<8>::khat_per_task;
     const size_t sh = p->nd == 16 ? Cfg<16>::shat_count : Cfg<8>::shat_count;
     const size_t scratch_bytes = (size_t)6 * a.N * sizeof(float);
-    p->batch = p->ntasks;
-    p->khat_bytes = (size_t)p->nsets * p->ntasks * per * sizeof(float2);
-    const uint32_t forced = getenv("ION_EB_FFT_BATCH") ? (uint32_t)atoi(getenv("ION_EB_FFT_BATCH")) : 0u;  // test hook: streamed mode with this batch
-    if (p->khat_bytes + scratch_bytes > budget_bytes || (forced > 0u && forced < p->ntasks)) {
-        // streamed mode: spectra for `batch` tasks at a time (at most ~1.7 GB per set, at least a few waves of blocks)
-        const uint32_t min_batch = p->ntasks < 1024u ? p->ntasks : 1024u;
-        if (!forced && scratch_bytes + ((size_t)p->nsets * min_batch * per * sizeof(float2)) > budget_bytes) { delete p; return cudaSuccess; }
-        size_t room = forced ? forced : (budget_bytes - scratch_bytes) / ((size_t)p->nsets * per * sizeof(float2));
+    // Which tasks own a slot of kernel spectra.  Preference: (1) every task, all slots resident (fastest products); (2) canonical tasks
+    // only, all slots resident (mirrored tasks read their partner's); (3) canonical tasks only, a buffer of `batch` slots refilled
+    // batch by batch inside every step (streamed).
+    const uint32_t forced = getenv("ION_EB_FFT_BATCH") ? (uint32_t)atoi(getenv("ION_EB_FFT_BATCH")) : 0u;  // test hook: streamed mode with this many slots
+    const int mirror_env = getenv("ION_EB_FFT_MIRROR") ? atoi(getenv("ION_EB_FFT_MIRROR")) : -1;       // test hook: 1 = mirrored even if (1) fits, 0 = never
+    const size_t slot_bytes = (size_t)p->nsets * per * sizeof(float2);
+    std::vector<Task> canon, mirr;  // mirr[i].kslot = index into canon for now
+    {
+        std::vector<uint32_t> canon_of(tasks.size(), 0xFFFFFFFFu);
+        for (size_t i = 0; i < tasks.size(); i++)
+            if (2u * tasks[i].ox <= p->g.dsx) { canon_of[i] = (uint32_t)canon.size(); canon.push_back(tasks[i]); }
+        // eb_fft_geometry emits ox fastest: the partner of task i sits at i - ox + (dsx - ox)
+        for (size_t i = 0; i < tasks.size(); i++)
+            if (2u * tasks[i].ox > p->g.dsx) {
+                Task t = tasks[i];
+                t.mirror = 1u;
+                t.kslot = canon_of[i - t.ox + (p->g.dsx - t.ox)];
+                mirr.push_back(t);
+            }
+    }
+    const bool fits_full = (size_t)p->ntasks * slot_bytes + scratch_bytes <= budget_bytes;
+    const bool fits_canon = canon.size() * slot_bytes + scratch_bytes <= budget_bytes;
+    const bool use_mirror = mirror_env != 0 && !mirr.empty() && (mirror_env == 1 || forced > 0u || !fits_full);
+    const uint32_t nslots_all = use_mirror ? (uint32_t)canon.size() : p->ntasks;
+    p->streamed = (forced > 0u && forced < nslots_all) || !(use_mirror ? fits_canon : fits_full);
+    p->batch = nslots_all;
+    if (p->streamed) {  // at most ~1.7 GB per set, at least a few waves of blocks
+        const uint32_t min_batch = nslots_all < 1024u ? nslots_all : 1024u;
+        if (!forced && scratch_bytes + (size_t)min_batch * slot_bytes > budget_bytes) { delete p; return cudaSuccess; }
+        size_t room = forced ? forced : (budget_bytes - scratch_bytes) / slot_bytes;
         if (room > 2048u) room = 2048u;
+        if (room > nslots_all) room = nslots_all;
         p->batch = (uint32_t)room;
-        if (p->batch > p->ntasks) p->batch = p->ntasks;
-        p->khat_bytes = (size_t)p->nsets * p->batch * per * sizeof(float2);
+        if (use_mirror) {  // a batch holds whole runs of x offsets, so that every mirrored task finds its partner's slot in the same batch
+            const uint32_t cpr = p->g.dsx / 2u + 1u;  // canonical tasks per run: ox = 0 .. dsx / 2
+            p->batch = p->batch / cpr * cpr;
+            if (p->batch < cpr) p->batch = cpr;
+        }
+    }
+    p->khat_bytes = (size_t)p->batch * slot_bytes;
+    {  // lay the task array out batch by batch
+        std::vector<Task> laid;
+        laid.reserve(tasks.size());
+        if (!use_mirror) {
+            for (size_t c0 = 0; c0 < tasks.size(); c0 += p->batch) {
+                const uint32_t nc = (uint32_t)(tasks.size() - c0 < p->batch ? tasks.size() - c0 : p->batch);
+                for (uint32_t i = 0; i < nc; i++) { Task t = tasks[c0 + i]; t.kslot = i; t.mirror = 0u; laid.push_back(t); }
+                p->batches.push_back(EbFftPlan::Batch{(uint32_t)c0, nc, (uint32_t)c0 + nc, 0u});
+            }
+        } else {
+            size_t mi = 0;  // mirr is ordered like canon (both follow the task order), so a batch's mirrored tasks are a contiguous run
+            for (size_t c0 = 0; c0 < canon.size(); c0 += p->batch) {
+                const uint32_t nc = (uint32_t)(canon.size() - c0 < p->batch ? canon.size() - c0 : p->batch);
+                EbFftPlan::Batch b;
+                b.c0 = (uint32_t)laid.size(); b.nc = nc;
+                for (uint32_t i = 0; i < nc; i++) { Task t = canon[c0 + i]; t.kslot = i; t.mirror = 0u; laid.push_back(t); }
+                b.m0 = (uint32_t)laid.size(); b.nm = 0u;
+                while (mi < mirr.size() && mirr[mi].kslot < c0 + nc) {
+                    Task t = mirr[mi++];
+                    t.kslot -= (uint32_t)c0;
+                    laid.push_back(t);
+                    b.nm++;
+                }
+                p->batches.push_back(b);
+            }
+        }
+        tasks.swap(laid);
     }
     far_set(a, p);
     {  // room for the pinned source spectra in L2 (a device-wide limit; a few MB of 126)
@@ -535,29 +603,42 @@ static void pin_source_spectra(const EbFftPlan* p, cudaStream_t s, size_t bytes,
     if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();  // best effort
 }
 
+template <int ND, int NSETS, int MIRROR> static void launch_fft(const EbFftPlan* p, uint32_t first, uint32_t count, cudaStream_t s) {
+    if (count == 0u) return;
+    const float2* k2 = NSETS == 2 ? p->khat + (size_t)p->batch * Cfg<ND>::khat_per_task : nullptr;
+    k_eb_fft<ND, NSETS, MIRROR><<<count, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks + first, p->khat, p->shat, k2, NSETS == 2 ? p->shatc : nullptr, p->scratch, 0);
+}
 template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& a, cudaStream_t s) {
     // function attributes are per device: set on every launch (a host-side table lookup)
-    cudaError_t e = p->nsets == 2 ? cudaFuncSetAttribute(k_eb_fft<ND, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem)
-                                  : cudaFuncSetAttribute(k_eb_fft<ND, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::main_smem);
+    cudaError_t e = cudaSuccess;
+    const int smem = (int)Cfg<ND>::main_smem;
+    if (p->nsets == 2) {
+        e = cudaFuncSetAttribute(k_eb_fft<ND, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eb_fft<ND, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    } else {
+        e = cudaFuncSetAttribute(k_eb_fft<ND, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_eb_fft<ND, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    }
     if (e != cudaSuccess) return e;
     const size_t kstride = (size_t)p->batch * Cfg<ND>::khat_per_task, sstride = Cfg<ND>::shat_count;
     for (int set = 0; set < p->nsets; set++)
         k_eb_src<ND><<<dim3(Cfg<ND>::H, 4), 128, 0, s>>>(p->g, p->sets[set], a.QU_lod, p->shat + (size_t)set * sstride, set == 1 ? p->shatc : nullptr);
-    const bool streamed = p->batch < p->ntasks;
-    if (streamed) {
+    if (p->streamed) {
         e = cudaFuncSetAttribute(k_eb_khat<ND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<ND>::khat_smem);
         if (e != cudaSuccess) return e;
     }
     pin_source_spectra(p, s, (size_t)p->nsets * sstride * sizeof(float2), true);
-    for (uint32_t t0 = 0; t0 < p->ntasks; t0 += p->batch) {
-        const uint32_t nt = p->ntasks - t0 < p->batch ? p->ntasks - t0 : p->batch;
-        if (streamed)
+    for (const EbFftPlan::Batch& b : p->batches) {
+        if (p->streamed)
             for (int set = 0; set < p->nsets; set++)
-                k_eb_khat<ND><<<dim3(nt, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks + t0, p->khat + (size_t)set * kstride);
-        if (p->nsets == 2)
-            k_eb_fft<ND, 2><<<nt, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks + t0, p->khat, p->shat, p->khat + kstride, p->shatc, p->scratch, 0);
-        else
-            k_eb_fft<ND, 1><<<nt, Cfg<ND>::T, Cfg<ND>::main_smem, s>>>(p->g, p->tasks + t0, p->khat, p->shat, nullptr, nullptr, p->scratch, 0);
+                k_eb_khat<ND><<<dim3(b.nc, 3), Cfg<ND>::KT, Cfg<ND>::khat_smem, s>>>(p->g, p->sets[set], p->tasks + b.c0, p->khat + (size_t)set * kstride);
+        if (p->nsets == 2) {
+            launch_fft<ND, 2, 0>(p, b.c0, b.nc, s);
+            launch_fft<ND, 2, 1>(p, b.m0, b.nm, s);
+        } else {
+            launch_fft<ND, 1, 0>(p, b.c0, b.nc, s);
+            launch_fft<ND, 1, 1>(p, b.m0, b.nm, s);
+        }
     }
     pin_source_spectra(p, s, 0, false);
     const uint32_t far_blocks = p->far_nbx * p->far_nby * p->far_nbz;
@@ -592,8 +673,9 @@ template <int ND> static cudaError_t launch_nd(const EbFftPlan* p, const KArgs& 
     return cudaGetLastError();
 }
 cudaError_t eb_fft_launch(const EbFftPlan* p, const KArgs& a, cudaStream_t s, uint64_t* launches) {
-    const uint64_t batches = (p->ntasks + p->batch - 1u) / p->batch;
-    *launches += 1u + (uint64_t)p->nsets + batches * (p->batch < p->ntasks ? 1u + (uint64_t)p->nsets : 1u) + (p->far_handled ? 2u : 0u);
+    uint64_t n = 1u + (uint64_t)p->nsets + (p->far_handled ? 2u : 0u);  // k_eb_combine, k_eb_src per set, the far-slab kernels
+    for (const EbFftPlan::Batch& b : p->batches) n += (p->streamed ? (uint64_t)p->nsets : 0u) + (b.nc ? 1u : 0u) + (b.nm ? 1u : 0u);
+    *launches += n;
     return p->nd == 16 ? launch_nd<16>(p, a, s) : launch_nd<8>(p, a, s);
 }
 size_t eb_fft_plan_bytes(const EbFftPlan* p) { return p ? p->khat_bytes : 0; }

@@ -61,8 +61,12 @@ struct SourceSet {
     float offx, offy, offz;
 };
 // one polyphase problem: the cells (b*ds + o) with z blocks [ND*wz, ND*wz + ND)
+// `kslot`: which entry of the kernel-spectrum buffer the task's products read (its own, or -- mirror != 0 -- the one of the task
+// with x offset dsx - ox, see main_phase_product_mirror)
 struct Task {
     uint16_t ox, oy, oz, wz;
+    uint32_t kslot;
+    uint32_t mirror;
 };
 
 template <int ND> struct Cfg {
@@ -426,6 +430,124 @@ template <int ND> ION_HD void main_phase_product2(int tid, const float2* shat, c
             w[3 * C::SLOT] = make_float2(B0.x + b0.x, B0.y + b0.y);
             w[4 * C::SLOT] = make_float2(B1.x + b1.x, B1.y + b1.y);
             w[5 * C::SLOT] = make_float2(B2.x + b2.x, B2.y + b2.y);
+        }
+    }
+}
+// ------------------------------------------------------------------------------------------------------
+// Mirror symmetry of the kernel in the in-block offset along x.  A cell with offset ox' = dsx - ox sees the own-level sources at
+// r'(d) = (-r_x(-d_x), r_y(d_y), r_z(d_z)) -- the positions of offset ox reflected -- and the neighbour's level (kind 1, centres on
+// block edges) at r'_x(d_x) = -r_x(-d_x - 1).  With K real that is, in frequency space,
+//     K^'_c(kx, ky, kz) = s_c conj(K^_c(kx, -ky, -kz))                        s_x = -1, s_y = s_z = +1,
+// times e^{+2 pi i kx / M} for the neighbour's level: a task with 2 ox > dsx needs no kernel spectrum of its own, it reads its
+// partner's slots at the reflected in-plane index.  (The circular index d_x = -ND, which no output uses, is the only kernel sample the
+// two forms disagree on; the fields differ by rounding only.)  Because the products overwrite the operands in place, a thread forms
+// the products of a point f = (kz, ky) and of its reflection g = (-kz, -ky) together: both are read before either is written.
+// ------------------------------------------------------------------------------------------------------
+ION_HD float2 conj_sign(float2 k, float sign) { return make_float2(sign * k.x, -(sign * k.y)); }
+template <int ND> ION_HD void main_phase_product_mirror(int tid, const float2* S0, int np, float2* W) {
+    typedef Cfg<ND> C;
+    constexpr int MM = C::M * C::M;
+    for (int idx = tid; idx < np * MM; idx += C::T) {
+        const int p = idx / MM, f = idx % MM;
+        const int kz = f / C::M, ky = f % C::M;
+        const int gz = (C::M - kz) & (C::M - 1), gy = (C::M - ky) & (C::M - 1);
+        if (gz * C::M + gy < f) continue;  // the pair belongs to the thread that holds the smaller index
+        const int of = kz * C::ROW + ky, og = gz * C::ROW + gy;
+        float2* w = W + (size_t)p * C::PLANE;
+        const float2* s0p = S0 + (size_t)p * C::SLOT;
+        float2 kf[3], kg[3], sf[4], sg[4];
+        sf[0] = s0p[of]; sg[0] = s0p[og];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            kf[c] = w[(size_t)c * C::SLOT + of]; kg[c] = w[(size_t)c * C::SLOT + og];
+            sf[1 + c] = w[(size_t)(3 + c) * C::SLOT + of]; sg[1 + c] = w[(size_t)(3 + c) * C::SLOT + og];
+        }
+        // the mirrored task's kernel at f is the partner's at g (and the other way round)
+        const float2 mf[3] = {conj_sign(kg[0], -1.0f), conj_sign(kg[1], 1.0f), conj_sign(kg[2], 1.0f)};
+        const float2 mg[3] = {conj_sign(kf[0], -1.0f), conj_sign(kf[1], 1.0f), conj_sign(kf[2], 1.0f)};
+#pragma unroll
+        for (int c = 0; c < 3; c++) w[(size_t)c * C::SLOT + of] = cmul(mf[c], sf[0]);
+        w[3 * C::SLOT + of] = cmul_sub(sf[2], mf[2], sf[3], mf[1]);  // (w x K)_x = w_y K_z - w_z K_y   (sim.cl:935)
+        w[4 * C::SLOT + of] = cmul_sub(sf[3], mf[0], sf[1], mf[2]);
+        w[5 * C::SLOT + of] = cmul_sub(sf[1], mf[1], sf[2], mf[0]);
+        if (og != of) {
+#pragma unroll
+            for (int c = 0; c < 3; c++) w[(size_t)c * C::SLOT + og] = cmul(mg[c], sg[0]);
+            w[3 * C::SLOT + og] = cmul_sub(sg[2], mg[2], sg[3], mg[1]);
+            w[4 * C::SLOT + og] = cmul_sub(sg[3], mg[0], sg[1], mg[2]);
+            w[5 * C::SLOT + og] = cmul_sub(sg[1], mg[1], sg[2], mg[0]);
+        }
+    }
+}
+// the same with two source sets: K^ of the own level in the E slots, K^' of the neighbour's level in the B slots, both of the
+// PARTNER task; tw = the table of main_tw4 (entry (kx, 0) holds cos and -sin of 2 pi kx / M)
+template <int ND> ION_HD void main_phase_product2_mirror(int tid, const float2* shat, const float2* S2c, const float4* tw, int kx0, int np, float2* W) {
+    typedef Cfg<ND> C;
+    constexpr int MM = C::M * C::M;
+    constexpr size_t CS = (size_t)C::H * C::SLOT;
+    for (int idx = tid; idx < np * MM; idx += C::T) {
+        const int p = idx / MM, f = idx % MM;
+        const int kz = f / C::M, ky = f % C::M;
+        const int gz = (C::M - kz) & (C::M - 1), gy = (C::M - ky) & (C::M - 1);
+        if (gz * C::M + gy < f) continue;
+        const int of = kz * C::ROW + ky, og = gz * C::ROW + gy;
+        const size_t base = (size_t)(kx0 + p) * C::SLOT;
+        float2 sf[4], sg[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            sf[j] = ION_LDG2(shat + (size_t)j * CS + base + of);
+            sg[j] = ION_LDG2(shat + (size_t)j * CS + base + og);
+        }
+        float2* w = W + (size_t)p * C::PLANE;
+        float2 kf[3], kg[3], lf[3], lg[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            kf[c] = w[(size_t)c * C::SLOT + of]; kg[c] = w[(size_t)c * C::SLOT + og];
+            lf[c] = w[(size_t)(3 + c) * C::SLOT + of]; lg[c] = w[(size_t)(3 + c) * C::SLOT + og];
+        }
+        // s^' from its compact form: sign flips when kz or ky leaves [0, ND)
+        const float sgf = ((kz >= ND) != (ky >= ND)) ? -1.0f : 1.0f, sgg = ((gz >= ND) != (gy >= ND)) ? -1.0f : 1.0f;
+        const float2* cf = S2c + (size_t)p * 4 * C::CSLOT + (kz & (ND - 1)) * ND + (ky & (ND - 1));
+        const float2* cg = S2c + (size_t)p * 4 * C::CSLOT + (gz & (ND - 1)) * ND + (gy & (ND - 1));
+        float2 tf[4], tg[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float2 a = cf[(size_t)j * C::CSLOT], b = cg[(size_t)j * C::CSLOT];
+            tf[j] = make_float2(sgf * a.x, sgf * a.y);
+            tg[j] = make_float2(sgg * b.x, sgg * b.y);
+        }
+        const float4 t4 = tw[(size_t)(kx0 + p) * (ND / 2)];
+        const float2 ph = make_float2(t4.y, -t4.w);  // e^{+2 pi i kx / M}
+        float2 mf[3], mg[3], nf[3], ng[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float sc = c == 0 ? -1.0f : 1.0f;
+            mf[c] = conj_sign(kg[c], sc); mg[c] = conj_sign(kf[c], sc);
+            nf[c] = cmul(ph, conj_sign(lg[c], sc)); ng[c] = cmul(ph, conj_sign(lf[c], sc));
+        }
+        {
+            const float2 E0 = cmul(mf[0], sf[0]), E1 = cmul(mf[1], sf[0]), E2 = cmul(mf[2], sf[0]);
+            const float2 B0 = cmul_sub(sf[2], mf[2], sf[3], mf[1]), B1 = cmul_sub(sf[3], mf[0], sf[1], mf[2]), B2 = cmul_sub(sf[1], mf[1], sf[2], mf[0]);
+            const float2 e0 = cmul(nf[0], tf[0]), e1 = cmul(nf[1], tf[0]), e2 = cmul(nf[2], tf[0]);
+            const float2 b0 = cmul_sub(tf[2], nf[2], tf[3], nf[1]), b1 = cmul_sub(tf[3], nf[0], tf[1], nf[2]), b2 = cmul_sub(tf[1], nf[1], tf[2], nf[0]);
+            w[of] = make_float2(E0.x + e0.x, E0.y + e0.y);
+            w[C::SLOT + of] = make_float2(E1.x + e1.x, E1.y + e1.y);
+            w[2 * C::SLOT + of] = make_float2(E2.x + e2.x, E2.y + e2.y);
+            w[3 * C::SLOT + of] = make_float2(B0.x + b0.x, B0.y + b0.y);
+            w[4 * C::SLOT + of] = make_float2(B1.x + b1.x, B1.y + b1.y);
+            w[5 * C::SLOT + of] = make_float2(B2.x + b2.x, B2.y + b2.y);
+        }
+        if (og != of) {
+            const float2 E0 = cmul(mg[0], sg[0]), E1 = cmul(mg[1], sg[0]), E2 = cmul(mg[2], sg[0]);
+            const float2 B0 = cmul_sub(sg[2], mg[2], sg[3], mg[1]), B1 = cmul_sub(sg[3], mg[0], sg[1], mg[2]), B2 = cmul_sub(sg[1], mg[1], sg[2], mg[0]);
+            const float2 e0 = cmul(ng[0], tg[0]), e1 = cmul(ng[1], tg[0]), e2 = cmul(ng[2], tg[0]);
+            const float2 b0 = cmul_sub(tg[2], ng[2], tg[3], ng[1]), b1 = cmul_sub(tg[3], ng[0], tg[1], ng[2]), b2 = cmul_sub(tg[1], ng[1], tg[2], ng[0]);
+            w[og] = make_float2(E0.x + e0.x, E0.y + e0.y);
+            w[C::SLOT + og] = make_float2(E1.x + e1.x, E1.y + e1.y);
+            w[2 * C::SLOT + og] = make_float2(E2.x + e2.x, E2.y + e2.y);
+            w[3 * C::SLOT + og] = make_float2(B0.x + b0.x, B0.y + b0.y);
+            w[4 * C::SLOT + og] = make_float2(B1.x + b1.x, B1.y + b1.y);
+            w[5 * C::SLOT + og] = make_float2(B2.x + b2.x, B2.y + b2.y);
         }
     }
 }

@@ -272,6 +272,47 @@ def test_streamed_kernel_spectra_give_the_same_fields(gpu_lib, monkeypatch):
             assert same_bits(e0, e1) and same_bits(b0, b1), name
 
 
+def test_mirrored_kernel_spectra(gpu_lib, monkeypatch):
+    """Tasks with 2 ox > dsx read the kernel spectra of their partner (x offset dsx - ox) at the reflected in-plane index instead of
+    owning a slot (eb_fft_core.cuh::main_phase_product_mirror; taken whenever the full set of spectra does not fit).  A split lattice
+    with four cells per LOD block along x (own level AND the neighbour's level, which mirrors with a one-block shift): the mirrored
+    static mode holds 3/4 of the spectra and agrees with the plain static mode to rounding (the two forms differ in one kernel sample
+    that no output uses); the streamed mode with mirroring is bit-identical to the mirrored static mode."""
+    cfg = cases._mhd(cases.C(velocity_set="D3Q19", float_type="FP32", n_x=64, n_y=16, n_z=64, d_z=2, nu=0.05, ext_volume_force=True,
+                             ext_magneto_hydro=True, mhd_lod_depth=4), 32.0)
+    ref = rh.RefLbm(cfg, threads=1, backend="port")
+    cases.fill_inputs(ref, cfg)
+    out, info = {}, {}
+    for mode, env in (("plain", {}), ("mirrored", {"ION_EB_FFT_MIRROR": "1"}), ("streamed", {"ION_EB_FFT_BATCH": "3"})):
+        for k in ("ION_EB_FFT_MIRROR", "ION_EB_FFT_BATCH"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        gpu = product(cfg)
+        cases.upload_inputs(ref, gpu)
+        gpu.initialize()
+        for i, rd in enumerate(ref.domains):
+            gpu.domains[i].write(cases.FIELD_OF["ei"], cases.electron_gas_at_rest(rd, cfg))
+        gpu.do_time_step()
+        gpu.do_time_step()
+        gpu.finish_queues()
+        info[mode] = [d.eb_fft_info() for d in gpu.domains]
+        out[mode] = [(d.read(cases.FIELD_OF["e_dyn"]).copy(), d.read(cases.FIELD_OF["b_dyn"]).copy()) for d in gpu.domains]
+        gpu.close()
+    for k in ("ION_EB_FFT_MIRROR", "ION_EB_FFT_BATCH"):
+        monkeypatch.delenv(k, raising=False)
+    for i in range(2):
+        assert info["plain"][i][1] == 12 and info["mirrored"][i][1] == 12, info           # tasks per slab: (2 + 1) z offsets x 4 x offsets
+        assert info["mirrored"][i][0] * 12 == info["plain"][i][0] * 9, info               # 9 of 12 tasks own a slot
+        assert info["streamed"][i][0] * 3 == info["mirrored"][i][0], info                 # a buffer of 3 slots
+        for c in range(2):
+            assert np.isfinite(out["plain"][i][c]).all()
+            assert rel_l2(out["mirrored"][i][c], out["plain"][i][c]) < 1e-6, (i, c)
+            assert same_bits(out["streamed"][i][c], out["mirrored"][i][c]), (i, c)
+        assert float(np.abs(out["plain"][i][0]).max()) > 0.0  # (B_dyn may vanish: the electron gas starts at rest)
+        assert not same_bits(out["mirrored"][i][0], out["plain"][i][0]), "the mirrored products must have run"
+
+
 MULTI = cases.multi_domain_cases()
 
 

@@ -219,13 +219,17 @@ def test_fp16c_encoder_identity_on_cpu(tmp_path):
     assert res["mismatches_non_nan"] == 0 and res["checked"] > 44_000_000
 
 
-@pytest.mark.parametrize("args", [("4", "32", "32", "34", "2"), ("3", "32", "16", "26", "2"), ("4", "16", "32", "16", "1")],
-                         ids=["depth4_slab_with_halo_window", "depth3_slab_with_halo_window", "depth4_single"])
+@pytest.mark.parametrize("args", [("4", "32", "32", "34", "2"), ("3", "32", "16", "26", "2"), ("4", "16", "32", "16", "1"),
+                                  ("3", "32", "16", "26", "2", "1"), ("3", "24", "16", "16", "1", "1")],
+                         ids=["depth4_slab_with_halo_window", "depth3_slab_with_halo_window", "depth4_single",
+                              "depth3_slab_mirrored_spectra_two_sets", "depth3_single_mirrored_spectra_odd_block"])
 def test_polyphase_fft_field_update_on_cpu(tmp_path, args):
     """update_e_b_dynamic as a polyphase FFT convolution (ionsolver_b200/csrc/eb_fft_core.cuh): the phase functions the CUDA
     kernels are made of are run thread by thread on the CPU (tests/tools/eb_fft_emul.cpp) and compared with a direct
     double-precision evaluation of the reference's own-LOD loop (sim_kernels.cl:940-955): window quirk Q5, self-skip, halo
-    layers, solid cells left untouched, the extra z window of halo-inclusive slabs.  Relative L2 below 1e-5 (measured 2e-7)."""
+    layers, solid cells left untouched, the extra z window of halo-inclusive slabs.  Relative L2 below 1e-5 (measured 2e-7).
+    The `mirrored` cases run the tasks with 2 ox > dsx on their partner's kernel spectra (main_phase_product_mirror /
+    main_phase_product2_mirror: reflection in frequency space, plus a one-block phase for the neighbour's level)."""
     import os
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -2,7 +2,7 @@
 // functions the CUDA kernels call, thread by thread, and compares E/B with a direct double-precision evaluation of the
 // reference's own-LOD loop (sim_kernels.cl:940-955).  Test infrastructure; built and run by tests/test_host_logic.py.
 //   g++ -O2 -std=c++17 -ffp-contract=off -I/usr/local/cuda/include tests/tools/eb_fft_emul.cpp -o eb_fft_emul
-//   eb_fft_emul <depth 3|4> <nx> <ny> <nz> <dz>
+//   eb_fft_emul <depth 3|4> <nx> <ny> <nz> <dz> [mirror: 1 = tasks with 2 ox > dsx read their partner's kernel spectra]
 #include <cstdio>
 #include <cstdlib>
 #include <cmath>
@@ -12,7 +12,7 @@
 
 using namespace ion::ebfft;
 
-template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t dz) {
+template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t dz, bool mirror) {
     typedef Cfg<ND> C;
     const uint32_t depth = ND == 16 ? 4 : 3;
     uint32_t n_lod_own = 0;
@@ -87,17 +87,33 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
                 for (int tid = 0; tid < 128; tid++) src_phase_z<ND>(tid, 128, kx, j, plane.data(), sh, set == 1 ? shat2c.data() : nullptr);
             }
     }
+    int mirrored = 0;
     for (int t = 0; t < ntasks; t++) {  // one pass: with two source sets their spectra are added before the inverse transform
-        const float2* kt = khat.data() + C::khat_per_task * t;
+        int ks = t;  // whose kernel spectra this task reads
+        const bool mir = mirror && 2u * tasks[t].ox > g.dsx;
+        if (mir) {
+            ks = -1;
+            for (int u = 0; u < ntasks; u++)
+                if (tasks[u].ox == g.dsx - tasks[t].ox && tasks[u].oy == tasks[t].oy && tasks[u].oz == tasks[t].oz && tasks[u].wz == tasks[t].wz) ks = u;
+            if (ks < 0) { printf("{\"error\": \"no mirror partner\"}\n"); return 2; }
+            mirrored++;
+        }
+        const float2* kt = khat.data() + C::khat_per_task * ks;
         std::fill(accreg.begin(), accreg.end(), 0.0f);
         for (int kx0 = 0; kx0 < C::H; kx0 += C::P) {
             const int np = C::H - kx0 < C::P ? C::H - kx0 : C::P;
             if (nsets == 2) {
-                main_stage2_host<ND>(kt, khat2.data() + C::khat_per_task * t, shat2c.data(), kx0, np, W.data(), S2c.data());
-                for (int tid = 0; tid < C::T; tid++) main_phase_product2<ND>(tid, shat.data(), S2c.data(), kx0, np, W.data());
+                main_stage2_host<ND>(kt, khat2.data() + C::khat_per_task * ks, shat2c.data(), kx0, np, W.data(), S2c.data());
+                for (int tid = 0; tid < C::T; tid++) {
+                    if (mir) main_phase_product2_mirror<ND>(tid, shat.data(), S2c.data(), tw.data(), kx0, np, W.data());
+                    else main_phase_product2<ND>(tid, shat.data(), S2c.data(), kx0, np, W.data());
+                }
             } else {
                 main_stage_host<ND>(kt, shat.data(), kx0, np, W.data(), S0.data());
-                for (int tid = 0; tid < C::T; tid++) main_phase_product<ND>(tid, S0.data(), np, W.data());
+                for (int tid = 0; tid < C::T; tid++) {
+                    if (mir) main_phase_product_mirror<ND>(tid, S0.data(), np, W.data());
+                    else main_phase_product<ND>(tid, S0.data(), np, W.data());
+                }
             }
             for (int tid = 0; tid < C::T; tid++) main_phase_z<ND>(tid, np, W.data());
             for (int tid = 0; tid < C::T; tid++) main_phase_y<ND>(tid, np, W.data());
@@ -167,7 +183,7 @@ template <int ND> static int run(uint32_t nx, uint32_t ny, uint32_t nz, uint32_t
                 checked++;
             }
     const double le = std::sqrt(num[0] / den[0]), lb = std::sqrt(num[1] / den[1]);
-    printf("{\"nd\": %d, \"source_sets\": %d, \"tasks\": %d, \"cells\": %ld, \"rel_l2_E\": %.3e, \"rel_l2_B\": %.3e, \"max_abs_err\": %.3e, \"untouched_bad\": %ld}\n", ND, nsets, ntasks,
+    printf("{\"nd\": %d, \"source_sets\": %d, \"tasks\": %d, \"mirrored_tasks\": %d, \"cells\": %ld, \"rel_l2_E\": %.3e, \"rel_l2_B\": %.3e, \"max_abs_err\": %.3e, \"untouched_bad\": %ld}\n", ND, nsets, ntasks, mirrored,
            checked, le, lb, maxerr, untouched_bad);
     return (le < 1e-5 && lb < 1e-5 && untouched_bad == 0) ? 0 : 1;
 }
@@ -176,5 +192,6 @@ int main(int argc, char** argv) {
     const int depth = argc > 1 ? atoi(argv[1]) : 4;
     const uint32_t nx = argc > 2 ? atoi(argv[2]) : 32, ny = argc > 3 ? atoi(argv[3]) : 32, nz = argc > 4 ? atoi(argv[4]) : 32;
     const uint32_t dz = argc > 5 ? atoi(argv[5]) : 1;
-    return depth == 4 ? run<16>(nx, ny, nz, dz) : run<8>(nx, ny, nz, dz);
+    const bool mirror = argc > 6 && atoi(argv[6]) != 0;
+    return depth == 4 ? run<16>(nx, ny, nz, dz, mirror) : run<8>(nx, ny, nz, dz, mirror);
 }
