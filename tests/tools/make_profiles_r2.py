@@ -193,7 +193,9 @@ def main():
     # the other configurations, the reference arm, the test logs: copied under fixed names
     for src, dst in (("r2_final_bench_cfg1.json", "r2_bench_cfg1.json"), ("r2_final_bench_cfg3.json", "r2_bench_cfg3.json"),
                      ("r2_final_bench_cfg4.json", "r2_bench_cfg4.json"), ("r2_final_bench_lod3.json", "r2_bench_lod3.json"),
-                     ("r2_final_bench_reference.json", "r2_bench_reference_arm.json")):
+                     ("r2_final_bench_reference.json", "r2_bench_reference_arm.json"), ("r2v_bench_cfg5.json", "r2_bench_cfg5_1gpu.json"),
+                     ("r2p_bench_cfg5.json", "r2_bench_cfg5_1gpu_unmirrored.json"), ("r2_final_cfg5_n8.json", "r2_bench_cfg5_n8_unmirrored.json"),
+                     ("r2v_bench_mirror.json", "r2_bench_mirror_forced.json")):
         p = first_existing(src)
         if p and load_line(p):
             json.dump(load_line(p), open(os.path.join(PRO, dst), "w"), indent=1)
@@ -202,7 +204,7 @@ def main():
         p = first_existing(src)
         if p:
             shutil.copy(p, os.path.join(PRO, dst))
-    big = [load_line(p) for p in (first_existing("r2_final_cfg4_n8.json"), first_existing("r2_final_cfg5_n8.json"), first_existing("r2_final_bench_cfg4.json")) if p]
+    big = [load_line(p) for p in (first_existing("r2_final_cfg4_n8.json"), first_existing("r2_final_cfg5_n8_mirror.json", "r2_final_cfg5_n8.json"), first_existing("r2_final_bench_cfg4.json")) if p]
     if len(big) == 3:
         with open(os.path.join(PRO, "r2_scaling_cfg4_cfg5_n8.jsonl"), "w") as f:
             for j in big:
