@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "eb_fft_core.cuh"
+#include "eb_fft_layout.hpp"
 #include "lattice.cuh"
 
 namespace ion {
@@ -494,20 +495,8 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
     const uint32_t forced = getenv("ION_EB_FFT_BATCH") ? (uint32_t)atoi(getenv("ION_EB_FFT_BATCH")) : 0u;  // test hook: streamed mode with this many slots
     const int mirror_env = getenv("ION_EB_FFT_MIRROR") ? atoi(getenv("ION_EB_FFT_MIRROR")) : -1;       // test hook: 1 = mirrored even if (1) fits, 0 = never
     const size_t slot_bytes = (size_t)p->nsets * per * sizeof(float2);
-    std::vector<Task> canon, mirr;  // mirr[i].kslot = index into canon for now
-    {
-        std::vector<uint32_t> canon_of(tasks.size(), 0xFFFFFFFFu);
-        for (size_t i = 0; i < tasks.size(); i++)
-            if (2u * tasks[i].ox <= p->g.dsx) { canon_of[i] = (uint32_t)canon.size(); canon.push_back(tasks[i]); }
-        // eb_fft_geometry emits ox fastest: the partner of task i sits at i - ox + (dsx - ox)
-        for (size_t i = 0; i < tasks.size(); i++)
-            if (2u * tasks[i].ox > p->g.dsx) {
-                Task t = tasks[i];
-                t.mirror = 1u;
-                t.kslot = canon_of[i - t.ox + (p->g.dsx - t.ox)];
-                mirr.push_back(t);
-            }
-    }
+    std::vector<Task> canon, mirr;
+    split_mirror_tasks(tasks, p->g.dsx, canon, mirr);
     const bool fits_full = (size_t)p->ntasks * slot_bytes + scratch_bytes <= budget_bytes;
     const bool fits_canon = canon.size() * slot_bytes + scratch_bytes <= budget_bytes;
     const bool use_mirror = mirror_env != 0 && !mirr.empty() && (mirror_env == 1 || forced > 0u || !fits_full);
@@ -521,39 +510,14 @@ cudaError_t eb_fft_create(const KArgs& a, size_t budget_bytes, cudaStream_t s, E
         if (room > 2048u) room = 2048u;
         if (room > nslots_all) room = nslots_all;
         p->batch = (uint32_t)room;
-        if (use_mirror) {  // a batch holds whole runs of x offsets, so that every mirrored task finds its partner's slot in the same batch
-            const uint32_t cpr = p->g.dsx / 2u + 1u;  // canonical tasks per run: ox = 0 .. dsx / 2
-            p->batch = p->batch / cpr * cpr;
-            if (p->batch < cpr) p->batch = cpr;
-        }
+        if (use_mirror) p->batch = mirror_batch_slots(p->batch, p->g.dsx);
     }
     p->khat_bytes = (size_t)p->batch * slot_bytes;
-    {  // lay the task array out batch by batch
+    {  // lay the task array out batch by batch (eb_fft_layout.hpp)
         std::vector<Task> laid;
-        laid.reserve(tasks.size());
-        if (!use_mirror) {
-            for (size_t c0 = 0; c0 < tasks.size(); c0 += p->batch) {
-                const uint32_t nc = (uint32_t)(tasks.size() - c0 < p->batch ? tasks.size() - c0 : p->batch);
-                for (uint32_t i = 0; i < nc; i++) { Task t = tasks[c0 + i]; t.kslot = i; t.mirror = 0u; laid.push_back(t); }
-                p->batches.push_back(EbFftPlan::Batch{(uint32_t)c0, nc, (uint32_t)c0 + nc, 0u});
-            }
-        } else {
-            size_t mi = 0;  // mirr is ordered like canon (both follow the task order), so a batch's mirrored tasks are a contiguous run
-            for (size_t c0 = 0; c0 < canon.size(); c0 += p->batch) {
-                const uint32_t nc = (uint32_t)(canon.size() - c0 < p->batch ? canon.size() - c0 : p->batch);
-                EbFftPlan::Batch b;
-                b.c0 = (uint32_t)laid.size(); b.nc = nc;
-                for (uint32_t i = 0; i < nc; i++) { Task t = canon[c0 + i]; t.kslot = i; t.mirror = 0u; laid.push_back(t); }
-                b.m0 = (uint32_t)laid.size(); b.nm = 0u;
-                while (mi < mirr.size() && mirr[mi].kslot < c0 + nc) {
-                    Task t = mirr[mi++];
-                    t.kslot -= (uint32_t)c0;
-                    laid.push_back(t);
-                    b.nm++;
-                }
-                p->batches.push_back(b);
-            }
-        }
+        std::vector<TaskBatch> batches;
+        layout_tasks(tasks, canon, mirr, use_mirror, p->batch, laid, batches);
+        for (const TaskBatch& b : batches) p->batches.push_back(EbFftPlan::Batch{b.c0, b.nc, b.m0, b.nm});
         tasks.swap(laid);
     }
     far_set(a, p);

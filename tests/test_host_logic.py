@@ -267,6 +267,24 @@ def test_far_slab_taylor_path_on_cpu(tmp_path, farb, r_min, bound):
     assert res["taylor_err_rel"] < bound and res["x_reduced_err_rel"] < bound and res["forms_differ_rel"] < 1e-6, res
 
 
+def test_mirrored_task_layout_on_cpu(tmp_path):
+    """Host side of the mirrored / streamed kernel spectra (ionsolver_b200/csrc/eb_fft_layout.hpp, used by eb_fft.cu::eb_fft_create):
+    tests/tools/eb_layout_check.cpp lays out 768 combinations of block shape, extra z window and slot capacity and checks that every
+    task appears once, that a mirrored task's slot is the canonical task with x offset dsx - ox and equal (oy, oz, wz) in its own
+    batch, and that batches respect the capacity."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda_inc = "/usr/local/cuda/include"
+    if not os.path.isfile(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("CUDA headers not installed")
+    exe = tmp_path / "eb_layout_check"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I", cuda_inc, os.path.join(root, "tests", "tools", "eb_layout_check.cpp"), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    assert out.returncode == 0 and res["violations"] == 0 and res["layouts_checked"] >= 700, res
+
+
 def test_fft_precompute_geometry_in_numpy():
     """Index logic of the FFT precompute mode (mesh_kernels.cu::launch_precompute_fft), restated with numpy transforms: sources inside
     their bounding box [mn, mn + S), outputs 0 .. L-1, transform lengths P = smooth7(L + S - 1), kernel array K[j mod P] = G(j - mn) for
